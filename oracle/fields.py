@@ -1,0 +1,274 @@
+"""
+CPU oracle, stage 1: grid coordinates, analytic + random fields, same-type sum rule,
+and the TestSimulator sampling stage.  NumPy restatement of the reference arithmetic
+(test infrastructure only -- see oracle/__init__.py).  Canonical units: kpc, microgauss,
+cm^-3, rad.
+
+Reference lines restated (relative to /root/reference/imagine):
+  grid coordinates        fields/grid.py:229-275   (np.mgrid with n*1j slices)
+  cylindrical radius      fields/grid.py:124
+  ConstantMagneticField   fields/basic_fields.py:29-40
+  ConstantThermalElectrons fields/basic_fields.py:55-56
+  ExponentialThermalElectrons fields/basic_fields.py:81-88
+  RandomThermalElectrons  fields/basic_fields.py:111-127
+  CosThermalElectronDensity fields/test_field.py:36-43
+  NaiveGaussianMagneticField fields/test_field.py:84-96
+  same-type sum           simulators/simulator.py:166-178
+  TestSimulator.simulate  simulators/test_simulator.py:47-69
+
+The GPU generates its Gaussian components with counter-based Philox4x32-10 (defined
+here, `philox_normals`), so stochastic fields agree with the reference *in
+distribution*; `*_reference` functions restate the reference's MT19937 stream and are
+used for the CPU baseline timing and the distribution checks.
+"""
+import numpy as np
+
+# field kinds -- must match include/imagine_b200.h (IMB_FIELD_*)
+CONST_B, GAUSS_B, CONST_NE, EXP_NE, COS_NE, RANDOM_NE, CRE_ANALYTIC, CRE_CONST = range(8)
+
+TYPE_OF_KIND = {CONST_B: 'magnetic_field', GAUSS_B: 'magnetic_field',
+                CONST_NE: 'thermal_electron_density', EXP_NE: 'thermal_electron_density',
+                COS_NE: 'thermal_electron_density', RANDOM_NE: 'thermal_electron_density',
+                CRE_ANALYTIC: 'cosmic_ray_electron_density',
+                CRE_CONST: 'cosmic_ray_electron_density'}
+STOCHASTIC_KINDS = (GAUSS_B, RANDOM_NE)
+
+
+class Grid:
+    """UniformGrid, cartesian: vertex-centred, end-inclusive (grid.py:256-260)."""
+
+    def __init__(self, box, resolution):
+        self.box = np.asarray(box, dtype=np.float64).reshape(3, 2)
+        self.resolution = np.asarray(resolution, dtype=np.int64).reshape(3)
+
+    @property
+    def shape(self):
+        return tuple(int(n) for n in self.resolution)
+
+    @property
+    def ncell(self):
+        return int(np.prod(self.resolution))
+
+    def step(self, axis):
+        # numpy's mgrid: step = (stop-start)/float(n-1) when n != 1, else 1
+        n = int(self.resolution[axis])
+        lo, hi = self.box[axis]
+        return (hi - lo) / float(n - 1) if n != 1 else 1.0
+
+    def axis_coords(self, axis):
+        # mgrid evaluates index*step + start (two roundings, no fma)
+        n = int(self.resolution[axis])
+        return np.arange(n, dtype=np.float64) * self.step(axis) + self.box[axis, 0]
+
+    def xyz(self):
+        x, y, z = (self.axis_coords(a) for a in range(3))
+        return x[:, None, None], y[None, :, None], z[None, None, :]
+
+
+# ----------------------------------------------------------------------------- analytic
+def constant_B(grid, Bx, By, Bz):
+    out = np.empty(grid.shape + (3,))
+    out[..., 0], out[..., 1], out[..., 2] = Bx, By, Bz
+    return out
+
+
+def constant_ne(grid, ne):
+    return np.ones(grid.shape) * ne
+
+
+def exponential_ne(grid, n0, Re, he):
+    x, y, z = grid.xyz()
+    R = np.sqrt(x**2 + y**2)
+    return n0 * np.exp(-R / Re) * np.exp(-np.abs(z / he)) * np.ones(grid.shape)
+
+
+def cos_ne(grid, n0, a, alpha, b, beta, c, gamma):
+    x, y, z = grid.xyz()
+    return ((n0) * (1 + np.cos(a * x + alpha))
+            * (1 + np.cos(b * y + beta))
+            * (1 + np.cos(c * z + gamma))) * np.ones(grid.shape)
+
+
+def cre_analytic(grid, j0, r0, z0, r_sun):
+    """
+    NEW API surface (the reference's CosmicRayElectronDensityField is a stub,
+    base_fields.py:104-113).  Gridded CRE flux normalisation at the reference energy E0,
+    in [GeV m^2 s sr]^-1, WMAP-style disc: j0 * exp(-(R - r_sun)/r0) * sech^2(z/z0)
+    (parameter names of fields/hamx/cre_analytic.py:19-27).
+    """
+    x, y, z = grid.xyz()
+    R = np.sqrt(x**2 + y**2)
+    ch = np.cosh(z / z0)
+    return j0 * np.exp(-(R - r_sun) / r0) * (1.0 / (ch * ch)) * np.ones(grid.shape)
+
+
+def cre_const(grid, j0):
+    return np.ones(grid.shape) * j0
+
+
+# ------------------------------------------------------------- reference RNG (MT19937)
+def gaussian_B_reference(grid, a0, b0, seed):
+    """scipy.stats.norm(loc,scale).rvs(size, random_state=seed) == this (bit-identical)."""
+    rs = np.random.RandomState(int(seed))
+    return rs.standard_normal(grid.shape + (3,)) * b0 + a0
+
+
+def random_ne_reference(grid, mean, std, min_ne, seed):
+    rs = np.random.RandomState(int(seed))
+    out = rs.standard_normal(grid.shape) * std + mean
+    if np.isfinite(min_ne):
+        out[out < min_ne] = min_ne
+    return out
+
+
+# -------------------------------------------------------------- Philox4x32-10 (GPU RNG)
+_M0, _M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_W0, _W1 = 0x9E3779B9, 0xBB67AE85
+_MASK = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10 (Salmon et al. 2011).  Inputs/outputs uint32 arrays."""
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & _MASK for c in (c0, c1, c2, c3))
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    for r in range(10):
+        p0 = _M0 * c0
+        p1 = _M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & _MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & _MASK
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ np.uint64(k0)), lo1, (hi0 ^ c3 ^ np.uint64(k1)), lo0
+        k0 = (k0 + _W0) & 0xFFFFFFFF
+        k1 = (k1 + _W1) & 0xFFFFFFFF
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def _u52(hi, lo):
+    """(hi, lo) uint32 -> double in (0,1): ((hi<<20 | lo>>12) + 0.5) * 2^-52, exact."""
+    k = (hi.astype(np.uint64) << np.uint64(20)) | (lo.astype(np.uint64) >> np.uint64(12))
+    return (k.astype(np.float64) + 0.5) * (2.0 ** -52)
+
+
+def philox_normal_blocks(seed, stream, block_index):
+    """
+    Box-Muller pair for each Philox block.  counter = (block_lo, block_hi, stream, 0),
+    key = (seed_lo, seed_hi).  Returns (z0, z1) = r*(cos, sin)(2*pi*u2), r = sqrt(-2 ln u1).
+    """
+    b = np.asarray(block_index, dtype=np.uint64)
+    seed = int(seed)
+    x0, x1, x2, x3 = philox4x32_10(b & _MASK, b >> np.uint64(32),
+                                   np.full(b.shape, stream, dtype=np.uint64),
+                                   np.zeros(b.shape, dtype=np.uint64),
+                                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u1, u2 = _u52(x0, x1), _u52(x2, x3)
+    r = np.sqrt(-2.0 * np.log(u1))
+    ang = 2.0 * u2  # in units of pi, exact
+    return r * _cospi(ang), r * _sinpi(ang)
+
+
+def _reduce_pi(t):
+    # t in [0,2): exact reduction to quadrant q and f in [-0.25, 0.25]
+    q = np.rint(t * 2.0)
+    f = t - q * 0.5
+    return q.astype(np.int64) & 3, f
+
+
+def _cospi(t):
+    q, f = _reduce_pi(t)
+    c, s = np.cos(np.pi * f), np.sin(np.pi * f)
+    return np.choose(q, [c, -s, -c, s])
+
+
+def _sinpi(t):
+    q, f = _reduce_pi(t)
+    c, s = np.cos(np.pi * f), np.sin(np.pi * f)
+    return np.choose(q, [s, c, -s, -c])
+
+
+def philox_normals(seed, stream, count):
+    """Flat stream: value n = element (n & 1) of block (n >> 1)."""
+    nblk = (count + 1) // 2
+    z0, z1 = philox_normal_blocks(seed, stream, np.arange(nblk, dtype=np.uint64))
+    out = np.empty(2 * nblk)
+    out[0::2], out[1::2] = z0, z1
+    return out[:count]
+
+
+def gaussian_B_philox(grid, a0, b0, seed, stream):
+    z = philox_normals(seed, stream, 3 * grid.ncell).reshape(grid.shape + (3,))
+    return z * b0 + a0
+
+
+def random_ne_philox(grid, mean, std, min_ne, seed, stream):
+    out = philox_normals(seed, stream, grid.ncell).reshape(grid.shape) * std + mean
+    if np.isfinite(min_ne):
+        out[out < min_ne] = min_ne
+    return out
+
+
+# ------------------------------------------------------------------ descriptor evaluator
+def evaluate_fields(grid, descs, seeds, rng='philox'):
+    """
+    Mirror of the C-ABI ``imb_field_eval``.  ``descs`` = list of (kind, params, stream);
+    ``seeds`` = per-realisation seeds (global realisation order).  Same-type fields are
+    summed left to right (simulator.py:175-178).  Returns {field_type: array} where the
+    array has a leading realisation axis of length len(seeds) if any contributing field
+    is stochastic, else length 1.
+    """
+    nreal = len(seeds)
+    out = {}
+    for ftype in dict.fromkeys(TYPE_OF_KIND[k] for k, _, _ in descs):
+        mine = [d for d in descs if TYPE_OF_KIND[d[0]] == ftype]
+        stochastic = any(k in STOCHASTIC_KINDS for k, _, _ in mine)
+        reals = []
+        for r in range(nreal if stochastic else 1):
+            total = None
+            for kind, p, stream in mine:
+                if kind == CONST_B:
+                    f = constant_B(grid, *p[:3])
+                elif kind == GAUSS_B:
+                    f = (gaussian_B_philox(grid, p[0], p[1], seeds[r], stream) if rng == 'philox'
+                         else gaussian_B_reference(grid, p[0], p[1], seeds[r]))
+                elif kind == CONST_NE:
+                    f = constant_ne(grid, p[0])
+                elif kind == EXP_NE:
+                    f = exponential_ne(grid, *p[:3])
+                elif kind == COS_NE:
+                    f = cos_ne(grid, *p[:7])
+                elif kind == RANDOM_NE:
+                    f = (random_ne_philox(grid, p[0], p[1], p[2], seeds[r], stream) if rng == 'philox'
+                         else random_ne_reference(grid, p[0], p[1], p[2], seeds[r]))
+                elif kind == CRE_ANALYTIC:
+                    f = cre_analytic(grid, *p[:4])
+                elif kind == CRE_CONST:
+                    f = cre_const(grid, p[0])
+                else:
+                    raise ValueError(kind)
+                total = f if total is None else total + f
+            reals.append(total)
+        out[ftype] = np.stack(reals)
+    return out
+
+
+# --------------------------------------------------------------------- TestSimulator
+def test_simulator_sample(grid, B, ne, points, b_axis=1):
+    """
+    t = B[..., b_axis] * ne at the nearest vertex of each point (test_simulator.py:47-69;
+    scipy RegularGridInterpolator(method='nearest'), default bounds_error=True).
+    ``points`` is [P,3] (x,y,z in kpc).  Ties go to the lower vertex (norm_distance <= .5).
+    """
+    t = B[..., b_axis] * ne
+    points = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    idx = []
+    for a in range(3):
+        c = grid.axis_coords(a)
+        p = points[:, a]
+        if np.any(p < c[0]) or np.any(p > c[-1]):
+            raise ValueError('One of the requested xi is out of bounds in dimension %d' % a)
+        n = c.size
+        if n == 1:
+            idx.append(np.zeros(p.shape, dtype=np.int64))
+            continue
+        i = np.clip(np.searchsorted(c, p, side='right') - 1, 0, n - 2)
+        yi = (p - c[i]) / (c[i + 1] - c[i])
+        idx.append(np.where(yi <= .5, i, i + 1))
+    return t[tuple(idx)]
