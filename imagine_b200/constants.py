@@ -1,0 +1,30 @@
+"""
+Physical constants and host-side scalar coefficients of the LOS integrator (CGS).
+The literals are frozen and identical to oracle/los.py and csrc/los.cu.
+"""
+import math
+
+C_LIGHT = 2.99792458e10        # cm / s
+Q_E = 4.80320471e-10           # esu
+M_E = 9.10938356e-28           # g
+K_B = 1.38064852e-16           # erg / K
+GEV_ERG = 1.6021766208e-3      # erg
+KPC_CM = 3.0856775814913673e21  # cm
+MEC2_ERG = M_E * C_LIGHT * C_LIGHT
+RM_CONST = 0.812               # rad m^-2 / (cm^-3 uG pc), tutorials/tutorial_simulator.ipynb:81
+
+
+def sync_coefficient(p, nu_ghz, e0_gev):
+    """
+    K(p, nu): Rayleigh-Jeans brightness temperature [K] per unit
+    (cre [GeV m^2 s sr]^-1) * (Bperp[uG]^2)^((p+1)/4) * cm for a power-law CRE spectrum of
+    index p normalised at e0_gev (Rybicki & Lightman eq. 6.36).
+    """
+    nu = nu_ghz * 1.0e9
+    t_conv = C_LIGHT * C_LIGHT / (2.0 * K_B * nu * nu)
+    ptot = (math.sqrt(3.0) * Q_E ** 3 / (2.0 * math.pi * MEC2_ERG * (p + 1.0))
+            * math.gamma(p / 4.0 + 19.0 / 12.0) * math.gamma(p / 4.0 - 1.0 / 12.0)
+            * (2.0 * math.pi * M_E * C_LIGHT * nu / (3.0 * Q_E)) ** (-(p - 1.0) / 2.0))
+    c_gamma = ((4.0 * math.pi / C_LIGHT) * (e0_gev * GEV_ERG) ** p
+               * MEC2_ERG ** (1.0 - p) / (GEV_ERG * 1.0e4))
+    return t_conv * 0.5 * ptot * c_gamma * (1.0e-6) ** ((p + 1.0) / 2.0)

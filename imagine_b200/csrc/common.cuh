@@ -1,0 +1,145 @@
+// Shared device/host helpers for libimagine_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/imagine_b200.h"
+
+namespace imb {
+
+// ---- library state (api.cu) ---------------------------------------------------------
+struct State {
+  bool initialised = false;
+  int device = -1;
+  int sm_count = 148;
+  void* ws = nullptr;          // scratch workspace (device)
+  size_t ws_bytes = 0;
+  void* pinned = nullptr;      // small pinned host buffer for scalar read-back
+  size_t pinned_bytes = 0;
+  long long launches = 0;
+  char cuda_err[256] = {0};
+};
+State& state();
+int set_cuda_error(cudaError_t e, const char* where);
+int ensure_workspace(size_t bytes);   // grows state().ws; returns IMB_* code
+int check_init();
+
+#define IMB_CUDA(call)                                                     \
+  do {                                                                     \
+    cudaError_t _e = (call);                                               \
+    if (_e != cudaSuccess) return imb::set_cuda_error(_e, #call);          \
+  } while (0)
+
+#define IMB_LAUNCHED()                                                     \
+  do {                                                                     \
+    imb::state().launches++;                                               \
+    cudaError_t _e = cudaGetLastError();                                   \
+    if (_e != cudaSuccess) return imb::set_cuda_error(_e, "kernel launch");\
+  } while (0)
+
+#define IMB_TRY(expr)                          \
+  do {                                         \
+    int _rc = (expr);                          \
+    if (_rc != IMB_OK) return _rc;             \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// carve typed pointers out of the workspace
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+// ---- device helpers --------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// grid geometry as the kernels see it
+struct DevGrid {
+  double lo[3];
+  double step[3];      // (hi-lo)/(n-1), or 1.0 when n == 1   (numpy mgrid semantics)
+  double inv_step[3];  // (n-1)/(hi-lo)
+  int n[3];
+  long long ncell;
+};
+
+__device__ __forceinline__ double vertex_coord(const DevGrid& g, int axis, int i) {
+  // np.mgrid: index*step + start with two roundings (no fma) -> bit-identical coordinates
+  return __dadd_rn(__dmul_rn((double)i, g.step[axis]), g.lo[axis]);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Neumaier-compensated accumulator: keeps long reductions within ~1 ulp of exact
+struct Comp {
+  double s = 0.0, c = 0.0;
+  __device__ __forceinline__ void add(double x) {
+    double t = __dadd_rn(s, x);
+    if (fabs(s) >= fabs(x)) c = __dadd_rn(c, __dadd_rn(__dsub_rn(s, t), x));
+    else c = __dadd_rn(c, __dadd_rn(__dsub_rn(x, t), s));
+    s = t;
+  }
+  __device__ __forceinline__ double value() const { return s + c; }
+};
+
+// block-wide sum of a double; result valid in thread 0.  `smem` >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  double r = 0.0;
+  if (warp == 0) {
+    r = lane < nw ? smem[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+// ---- Philox4x32-10 (Salmon et al. 2011); oracle/fields.py:philox4x32_10 --------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {
+  const unsigned long long k = ((unsigned long long)hi << 20) | (unsigned long long)(lo >> 12);
+  return ((double)k + 0.5) * 2.220446049250313e-16;  // 2^-52
+}
+
+// Box-Muller pair of block `blk` of stream `stream` under `seed`
+__device__ __forceinline__ void philox_normal_pair(unsigned long long seed, uint32_t stream,
+                                                   unsigned long long blk, double& z0, double& z1) {
+  const uint4 x = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), stream, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const double u1 = u52(x.x, x.y), u2 = u52(x.z, x.w);
+  const double r = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+#endif  // __CUDACC__
+}  // namespace imb

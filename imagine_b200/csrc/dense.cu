@@ -1,0 +1,565 @@
+// Stage 3b: the dense covariance route.
+//   S = U^T U / N as a tensor-core GEMM (FP64 DMMA, mma.sync m8n8k4 -- tcgen05 has no f64
+//   kind), fused with the OAS shrinkage and the "+ measurement covariance" epilogue;
+//   blocked right-looking Cholesky (64-wide panels: tile factor in shared memory, triangular
+//   solve of the panel, DMMA trailing update); the right-hand side d rides along as an extra
+//   row, so z = L^-1 d falls out of the factorisation.  Non-symmetric or non-positive-definite
+//   input (the reference is LU throughout and its tests feed np.random.rand matrices,
+//   tests/test_likelihood.py:63-113) takes a partially pivoted LU instead.
+// Reference arithmetic: oracle/likelihood.py (empirical_mcov / oas_mcov / ensemble_loglike).
+#include "common.cuh"
+#include "linalg.cuh"
+
+namespace imb {
+
+constexpr int TB = 64;       // output tile edge / Cholesky panel width
+constexpr int KC = 16;       // k-chunk staged in shared memory
+constexpr int LDS_ = TB + 4; // smem leading dimension: conflict-free DMMA fragment loads
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// One 64x64 tile of acc = A * B^T over k in [0, K): warp w owns rows 8w..8w+7, all 8 column
+// blocks.  Operand element getters are functors so the same core serves SYRK and Cholesky.
+template <typename LoadA, typename LoadB>
+__device__ __forceinline__ void tile_mma(int K, LoadA loadA, LoadB loadB, double (&acc)[8][2],
+                                         double (*sA)[LDS_], double (*sB)[LDS_]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    for (int e = threadIdx.x; e < TB * KC; e += 256) {
+      int i, k;
+      loadA.index(e, i, k);
+      sA[k][i] = (k0 + k < K) ? loadA(i, k0 + k) : 0.0;
+      loadB.index(e, i, k);
+      sB[k][i] = (k0 + k < K) ? loadB(i, k0 + k) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC; kk += 4) {
+      const double a = sA[kk + fk][warp * 8 + fr];
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        const double b = sB[kk + fk][nb * 8 + fr];
+        dmma884(acc[nb][0], acc[nb][1], a, b);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- build A = M + cov_est(sims) --------------------------------------------------------
+// operand(i,k) = X[k*m + i0+i] - mean[i0+i]  (i contiguous)
+struct CenteredOperand {
+  const double* X; const double* mean; int m, N, i0;
+  __device__ __forceinline__ void index(int e, int& i, int& k) const { i = e & (TB - 1); k = e >> 6; }
+  __device__ __forceinline__ double operator()(int i, int k) const {
+    const int col = i0 + i;
+    return col < m ? X[(size_t)k * m + col] - mean[col] : 0.0;
+  }
+};
+
+// out[i*ld + j] = M_ij + ((1-rho) * S_ij + (i==j) * delta),  S = U^T U / N
+//   cov_kind: 0 none (M = 0), 1 variance (M = diag), 2 dense
+__global__ void __launch_bounds__(256) build_cov_kernel(const double* __restrict__ X, int N, int m,
+                                                        const double* __restrict__ mean,
+                                                        const LikeScalars* __restrict__ sc,
+                                                        const double* __restrict__ M, int cov_kind,
+                                                        double* __restrict__ out, int ld) {
+  __shared__ double sA[KC][LDS_];
+  __shared__ double sB[KC][LDS_];
+  double acc[8][2];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) acc[nb][0] = acc[nb][1] = 0.0;
+  const int i0 = blockIdx.y * TB, j0 = blockIdx.x * TB;
+  CenteredOperand A{X, mean, m, N, i0}, B{X, mean, m, N, j0};
+  tile_mma(N, A, B, acc, sA, sB);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double one_minus_rho = 1.0 - sc->rho, delta = sc->delta, n = (double)N;
+  const int i = i0 + warp * 8 + (lane >> 2);
+  if (i >= m) return;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = j0 + nb * 8 + 2 * (lane & 3) + h;
+      if (j >= m) continue;
+      const double s = __ddiv_rn(acc[nb][h], n);
+      const double cov = __dadd_rn(__dmul_rn(one_minus_rho, s), (i == j) ? delta : 0.0);
+      double mij = 0.0;
+      if (cov_kind == IMB_COV_DENSE) mij = M[(size_t)i * m + j];
+      else if (cov_kind == IMB_COV_VARIANCE) mij = (i == j) ? M[i] : 0.0;
+      out[(size_t)i * ld + j] = (cov_kind == IMB_COV_NONE) ? cov : __dadd_rn(mij, cov);
+    }
+  }
+}
+
+// out = M (+ diag(extra)) copied into a matrix with leading dimension ld
+__global__ void copy_cov_kernel(const double* __restrict__ M, int cov_kind, int m,
+                                const double* __restrict__ extra_diag, double* __restrict__ out, int ld) {
+  const long long total = (long long)m * m;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / m), j = (int)(e % m);
+    double v = 0.0;
+    if (cov_kind == IMB_COV_DENSE) v = M[e];
+    else if (cov_kind == IMB_COV_VARIANCE) v = (i == j) ? M[i] : 0.0;
+    if (extra_diag && i == j) v = (cov_kind == IMB_COV_NONE) ? extra_diag[i] : __dadd_rn(v, extra_diag[i]);
+    out[(size_t)i * ld + j] = v;
+  }
+}
+
+__global__ void place_rhs_kernel(const double* __restrict__ d, int m, double* __restrict__ dst, int stride) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    dst[(size_t)i * stride] = d[i];
+}
+
+// flag[0] = 1 if A (ld) is not exactly symmetric
+__global__ void symmetry_kernel(const double* __restrict__ A, int m, int ld, int* flag) {
+  const long long total = (long long)m * m;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / m), j = (int)(e % m);
+    if (j < i && A[(size_t)i * ld + j] != A[(size_t)j * ld + i]) *flag = 1;
+  }
+}
+
+// ---- blocked Cholesky (lower, in place, row-major, ld = m; rows 0..m, row m = rhs) ----------
+// factor the kb x kb diagonal tile at k0; pivots[k0+k] = value under the square root
+__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ A, int ld, int k0, int kb,
+                                                    double* __restrict__ pivots, int* __restrict__ info) {
+  __shared__ double T[TB][TB + 1];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < kb * kb; e += 256) {
+    const int i = e / kb, j = e % kb;
+    T[i][j] = A[(size_t)(k0 + i) * ld + k0 + j];
+  }
+  __syncthreads();
+  for (int k = 0; k < kb; ++k) {
+    if (tid == 0) {
+      const double p = T[k][k];
+      pivots[k0 + k] = p;
+      if (!(p > 0.0) && *info == 0) *info = k0 + k + 1;
+      T[k][k] = sqrt(p);
+    }
+    __syncthreads();
+    const double lkk = T[k][k];
+    for (int i = k + 1 + tid; i < kb; i += 256) T[i][k] /= lkk;
+    __syncthreads();
+    const int rem = kb - k - 1;
+    for (int e = tid; e < rem * rem; e += 256) {
+      const int i = k + 1 + e / rem, j = k + 1 + e % rem;
+      if (j <= i) T[i][j] -= T[i][k] * T[j][k];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < kb * kb; e += 256) {
+    const int i = e / kb, j = e % kb;
+    if (j <= i) A[(size_t)(k0 + i) * ld + k0 + j] = T[i][j];
+  }
+}
+
+// rows i in [k0+kb, nrows): A[i, k0:k0+kb] <- A[i, k0:k0+kb] * L11^-T ; 64 rows per block
+__global__ void __launch_bounds__(64) trsm_kernel(double* __restrict__ A, int ld, int k0, int kb,
+                                                  int nrows) {
+  extern __shared__ double sm[];
+  double (*L)[TB + 1] = reinterpret_cast<double (*)[TB + 1]>(sm);
+  double (*R)[TB + 1] = reinterpret_cast<double (*)[TB + 1]>(sm + TB * (TB + 1));
+  const int tid = threadIdx.x;
+  const int r0 = k0 + kb + blockIdx.x * TB;
+  for (int e = tid; e < kb * kb; e += 64) {
+    const int i = e / kb, j = e % kb;
+    L[i][j] = A[(size_t)(k0 + i) * ld + k0 + j];
+  }
+  for (int e = tid; e < TB * kb; e += 64) {
+    const int i = e / kb, j = e % kb;
+    R[i][j] = (r0 + i < nrows) ? A[(size_t)(r0 + i) * ld + k0 + j] : 0.0;
+  }
+  __syncthreads();
+  for (int c = 0; c < kb; ++c) {
+    double s = R[tid][c];
+    for (int j = 0; j < c; ++j) s -= R[tid][j] * L[c][j];
+    R[tid][c] = s / L[c][c];
+  }
+  __syncthreads();
+  for (int e = tid; e < TB * kb; e += 64) {
+    const int i = e / kb, j = e % kb;
+    if (r0 + i < nrows) A[(size_t)(r0 + i) * ld + k0 + j] = R[i][j];
+  }
+}
+
+// operand(i,k) = A[(r0+i)*ld + k0+k]  (k contiguous)
+struct PanelOperand {
+  const double* A; int ld, r0, k0, nrows;
+  __device__ __forceinline__ void index(int e, int& i, int& k) const { k = e & (KC - 1); i = e >> 4; }
+  __device__ __forceinline__ double operator()(int i, int k) const {
+    return (r0 + i < nrows) ? A[(size_t)(r0 + i) * ld + k0 + k] : 0.0;
+  }
+};
+
+// trailing update: A[i][j] -= sum_k A[i][k0+k] A[j][k0+k], i in [t0, nrows), j in [t0, m), tiles j<=i
+__global__ void __launch_bounds__(256) chol_update_kernel(double* __restrict__ A, int ld, int k0, int kb,
+                                                          int t0, int nrows, int m) {
+  if (blockIdx.x > blockIdx.y) return;
+  __shared__ double sA[KC][LDS_];
+  __shared__ double sB[KC][LDS_];
+  double acc[8][2];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) acc[nb][0] = acc[nb][1] = 0.0;
+  const int i0 = t0 + blockIdx.y * TB, j0 = t0 + blockIdx.x * TB;
+  PanelOperand Pa{A, ld, i0, k0, nrows}, Pb{A, ld, j0, k0, m};
+  tile_mma(kb, Pa, Pb, acc, sA, sB);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = i0 + warp * 8 + (lane >> 2);
+  if (i >= nrows) return;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = j0 + nb * 8 + 2 * (lane & 3) + h;
+      if (j < m && j <= i) A[(size_t)i * ld + j] -= acc[nb][h];
+    }
+}
+
+// ---- partially pivoted LU on the augmented matrix [A | d] (ld = m + 1) ------------------------
+__global__ void __launch_bounds__(1024) lu_pivot_kernel(double* __restrict__ A, int m, int ld, int k,
+                                                        double* __restrict__ pivots, int* __restrict__ info) {
+  __shared__ double sval[32];
+  __shared__ int sidx[32];
+  __shared__ int prow;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double best = -1.0;
+  int bi = k;
+  for (int i = k + tid; i < m; i += blockDim.x) {
+    const double v = fabs(A[(size_t)i * ld + k]);
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) { sval[warp] = best; sidx[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < (blockDim.x >> 5) ? sval[lane] : -1.0;
+    bi = lane < (blockDim.x >> 5) ? sidx[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) prow = bi;
+  }
+  __syncthreads();
+  const int p = prow;
+  if (p != k) {
+    for (int j = tid; j <= m; j += blockDim.x) {
+      const double a = A[(size_t)k * ld + j], b = A[(size_t)p * ld + j];
+      A[(size_t)k * ld + j] = b;
+      A[(size_t)p * ld + j] = a;
+    }
+  }
+  __syncthreads();
+  const double ukk = A[(size_t)k * ld + k];
+  if (tid == 0) {
+    pivots[k] = ukk;
+    if (p != k) info[1] ^= 1;                       // swap parity
+    if (ukk == 0.0 && info[0] == 0) info[0] = k + 1;  // exactly singular
+  }
+  for (int i = k + 1 + tid; i < m; i += blockDim.x) A[(size_t)i * ld + k] /= ukk;
+}
+
+__global__ void __launch_bounds__(256) lu_update_kernel(double* __restrict__ A, int m, int ld, int k) {
+  // A[i][j] -= l_i * u_j for i in (k, m), j in (k, m]  (column m = rhs)
+  const int j = k + 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > m) return;
+  const double ukj = A[(size_t)k * ld + j];
+  for (int i = k + 1 + blockIdx.y; i < m; i += gridDim.y)
+    A[(size_t)i * ld + j] -= A[(size_t)i * ld + k] * ukj;
+}
+
+// back substitution U x = y (y = column m), then quad = d . x ; single block
+__global__ void __launch_bounds__(1024) lu_backsolve_kernel(double* __restrict__ A, int m, int ld,
+                                                            const double* __restrict__ d,
+                                                            LikeScalars* __restrict__ sc) {
+  __shared__ double red[32];
+  __shared__ double xk;
+  const int tid = threadIdx.x;
+  for (int k = m - 1; k >= 0; --k) {
+    if (tid == 0) {
+      xk = A[(size_t)k * ld + m] / A[(size_t)k * ld + k];
+      A[(size_t)k * ld + m] = xk;
+    }
+    __syncthreads();
+    const double x = xk;
+    for (int i = tid; i < k; i += blockDim.x) A[(size_t)i * ld + m] -= A[(size_t)i * ld + k] * x;
+    __syncthreads();
+  }
+  Comp q;
+  for (int i = tid; i < m; i += blockDim.x) q.add(d[i] * A[(size_t)i * ld + m]);
+  const double v = block_sum(q.value(), red);
+  if (tid == 0) sc->quad = v;
+}
+
+// quad = || row m of the Cholesky workspace ||^2 ; single block
+__global__ void __launch_bounds__(1024) chol_quad_kernel(const double* __restrict__ z, int m,
+                                                         LikeScalars* __restrict__ sc) {
+  __shared__ double red[32];
+  Comp q;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) q.add(z[i] * z[i]);
+  const double v = block_sum(q.value(), red);
+  if (threadIdx.x == 0) sc->quad = v;
+}
+
+// logdet = sum_k log((|p_k| * 2) * pi) in a fixed order, sign = parity * prod sign(p_k);
+// then loglike = -1/2 (quad + sign * logdet).  use_abs = 0 mirrors numpy's log of the raw
+// value (trace approximation, sign forced to +1).  Single block.
+__global__ void __launch_bounds__(1024) logdet_finish_kernel(const double* __restrict__ piv, int m,
+                                                             int use_abs, const int* __restrict__ info,
+                                                             LikeScalars* __restrict__ sc, int have_quad) {
+  __shared__ double red[32];
+  Comp l;
+  double neg = 0.0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const double p = piv[i];
+    l.add(log(__dmul_rn(__dmul_rn(use_abs ? fabs(p) : p, 2.0), 3.141592653589793)));
+    if (p < 0.0) neg += 1.0;
+  }
+  const double ld = block_sum(l.value(), red);
+  const double ng = block_sum(neg, red);
+  if (threadIdx.x == 0) {
+    double sign = 1.0;
+    if (use_abs) {
+      long long flips = (long long)ng + (info ? info[1] : 0);
+      sign = (flips & 1) ? -1.0 : 1.0;
+    }
+    sc->logdet = ld;
+    sc->sign = sign;
+    if (have_quad) sc->loglike = -0.5 * (sc->quad + sign * ld);
+  }
+}
+
+__global__ void add_vec_kernel(const double* __restrict__ a, const double* __restrict__ b, int m,
+                               double* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    out[i] = __dadd_rn(a[i], b[i]);
+}
+
+__global__ void diag_of_kernel(const double* __restrict__ M, int m, double* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    out[i] = M[(size_t)i * m + i];
+}
+
+// ---- host orchestration ------------------------------------------------------------------
+struct DenseWs {
+  LikeScalars* sc;
+  int* info;          // [0] first bad pivot (1-based), [1] swap parity, [2] asymmetry flag
+  double *mean, *diff, *xvar, *tvec, *pivots, *G, *partial, *A;
+};
+
+static int carve_dense(int N, int m, DenseWs* w) {
+  const int slices = gram_slices(m);
+  const size_t a_elems = (size_t)(m + 1) * (m + 1);
+  const size_t need = 256 * 16 + sizeof(LikeScalars) + 64 +
+                      sizeof(double) * ((size_t)5 * m + (size_t)(slices + 1) * N * N + a_elems);
+  IMB_TRY(ensure_workspace(need));
+  Carver c(state().ws);
+  w->sc = c.take<LikeScalars>(1);
+  w->info = c.take<int>(4);
+  w->mean = c.take<double>(m);
+  w->diff = c.take<double>(m);
+  w->xvar = c.take<double>(m);
+  w->tvec = c.take<double>(m);
+  w->pivots = c.take<double>(m);
+  w->G = c.take<double>((size_t)N * N);
+  w->partial = c.take<double>((size_t)slices * N * N);
+  w->A = c.take<double>(a_elems);
+  return IMB_OK;
+}
+
+// writes A (leading dimension ld) = meas_cov + estimator covariance of sims
+static int build_matrix(const double* sims, int N, int m, const double* cov, int cov_kind,
+                        int estimator, int ensemble, DenseWs& w, int ld, cudaStream_t s) {
+  if (!ensemble) {
+    copy_cov_kernel<<<grid_blocks((long long)m * m, 256, 8), 256, 0, s>>>(cov, cov_kind, m, nullptr, w.A, ld);
+    IMB_LAUNCHED();
+  } else if (estimator == IMB_EST_DIAGONAL) {
+    copy_cov_kernel<<<grid_blocks((long long)m * m, 256, 8), 256, 0, s>>>(cov, cov_kind, m, w.xvar, w.A, ld);
+    IMB_LAUNCHED();
+  } else {
+    const int nt = (m + TB - 1) / TB;
+    build_cov_kernel<<<dim3(nt, nt), 256, 0, s>>>(sims, N, m, w.mean, w.sc, cov, cov_kind, w.A, ld);
+    IMB_LAUNCHED();
+  }
+  return IMB_OK;
+}
+
+static int cholesky(DenseWs& w, int m, cudaStream_t s) {
+  const int ld = m, nrows = m + 1;
+  static bool attr_set = false;
+  const size_t trsm_smem = sizeof(double) * 2 * TB * (TB + 1);
+  if (!attr_set) {
+    IMB_CUDA(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem));
+    attr_set = true;
+  }
+  for (int k0 = 0; k0 < m; k0 += TB) {
+    const int kb = (m - k0) < TB ? (m - k0) : TB;
+    potf2_kernel<<<1, 256, 0, s>>>(w.A, ld, k0, kb, w.pivots, w.info);
+    IMB_LAUNCHED();
+    const int t0 = k0 + kb;
+    const int rows_below = nrows - t0;
+    if (rows_below <= 0) break;
+    trsm_kernel<<<(rows_below + TB - 1) / TB, 64, trsm_smem, s>>>(w.A, ld, k0, kb, nrows);
+    IMB_LAUNCHED();
+    if (t0 < m) {
+      const int nty = (nrows - t0 + TB - 1) / TB, ntx = (m - t0 + TB - 1) / TB;
+      chol_update_kernel<<<dim3(ntx, nty), 256, 0, s>>>(w.A, ld, k0, kb, t0, nrows, m);
+      IMB_LAUNCHED();
+    }
+  }
+  return IMB_OK;
+}
+
+static int lu(DenseWs& w, int m, cudaStream_t s) {
+  const int ld = m + 1;
+  for (int k = 0; k < m; ++k) {
+    lu_pivot_kernel<<<1, m - k >= 4096 ? 1024 : 256, 0, s>>>(w.A, m, ld, k, w.pivots, w.info);
+    IMB_LAUNCHED();
+    const int cols = m - k;  // columns k+1 .. m inclusive
+    if (k + 1 < m) {
+      const int rows = m - k - 1;
+      const int gy = rows < 64 ? rows : (rows < 2048 ? 64 : 256);
+      lu_update_kernel<<<dim3((cols + 255) / 256, gy), 256, 0, s>>>(w.A, m, ld, k);
+      IMB_LAUNCHED();
+    }
+  }
+  return IMB_OK;
+}
+
+int loglike_dense(const double* sims, int N, int m, const double* meas, const double* cov,
+                  int cov_kind, int estimator, int use_trace_approximation, int ensemble,
+                  double* out_loglike, int32_t* out_info, cudaStream_t s) {
+  DenseWs w;
+  IMB_TRY(carve_dense(N, m, &w));
+  IMB_CUDA(cudaMemsetAsync(w.info, 0, 4 * sizeof(int), s));
+  IMB_TRY(launch_colmean(sims, N, m, meas, w.mean, w.diff, s));
+  if (ensemble) {
+    if (estimator == IMB_EST_DIAGONAL || use_trace_approximation) IMB_TRY(launch_colvar(sims, N, m, w.xvar, s));
+    if (estimator != IMB_EST_DIAGONAL) {
+      IMB_TRY(launch_gram(sims, N, m, w.mean, nullptr, w.partial, w.G, s));
+      IMB_TRY(launch_oas_scalars(w.G, N, m, estimator, w.sc, s));
+    }
+  }
+  // symmetric input -> try Cholesky first (A = M + symmetric PSD estimate)
+  bool try_chol = true;
+  if (cov_kind == IMB_COV_DENSE) {
+    symmetry_kernel<<<grid_blocks((long long)m * m, 256, 8), 256, 0, s>>>(cov, m, m, w.info + 2);
+    IMB_LAUNCHED();
+    int* h = static_cast<int*>(state().pinned);
+    IMB_CUDA(cudaMemcpyAsync(h, w.info + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
+    IMB_CUDA(cudaStreamSynchronize(s));
+    try_chol = (*h == 0);
+  }
+  int bits = IMB_INFO_ROUTE_DENSE;
+  int lapack_info = 0;
+  bool done = false;
+  if (try_chol) {
+    IMB_TRY(build_matrix(sims, N, m, cov, cov_kind, estimator, ensemble, w, m, s));
+    place_rhs_kernel<<<grid_blocks(m, 256, 4), 256, 0, s>>>(w.diff, m, w.A + (size_t)m * m, 1);
+    IMB_LAUNCHED();
+    IMB_TRY(cholesky(w, m, s));
+    int* h = static_cast<int*>(state().pinned);
+    IMB_CUDA(cudaMemcpyAsync(h, w.info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    IMB_CUDA(cudaStreamSynchronize(s));
+    if (*h == 0) {
+      chol_quad_kernel<<<1, 1024, 0, s>>>(w.A + (size_t)m * m, m, w.sc);
+      IMB_LAUNCHED();
+      bits |= IMB_INFO_CHOLESKY;
+      done = true;
+    } else {
+      lapack_info = *h;   // not positive definite: fall through to LU
+      IMB_CUDA(cudaMemsetAsync(w.info, 0, 4 * sizeof(int), s));
+    }
+  }
+  if (!done) {
+    IMB_TRY(build_matrix(sims, N, m, cov, cov_kind, estimator, ensemble, w, m + 1, s));
+    place_rhs_kernel<<<grid_blocks(m, 256, 4), 256, 0, s>>>(w.diff, m, w.A + m, m + 1);
+    IMB_LAUNCHED();
+    IMB_TRY(lu(w, m, s));
+    lu_backsolve_kernel<<<1, 1024, 0, s>>>(w.A, m, m + 1, w.diff, w.sc);
+    IMB_LAUNCHED();
+    bits |= IMB_INFO_LU;
+  }
+  if (ensemble && use_trace_approximation) {
+    // logdet ~ sum log(2 pi (meas_var + X.var(0))), sign = +1 (ensemble_likelihood.py:100-103)
+    if (cov_kind == IMB_COV_DENSE) {
+      diag_of_kernel<<<grid_blocks(m, 256, 4), 256, 0, s>>>(cov, m, w.tvec);
+      IMB_LAUNCHED();
+      add_vec_kernel<<<grid_blocks(m, 256, 4), 256, 0, s>>>(w.tvec, w.xvar, m, w.tvec);
+    } else {
+      add_vec_kernel<<<grid_blocks(m, 256, 4), 256, 0, s>>>(cov, w.xvar, m, w.tvec);
+    }
+    IMB_LAUNCHED();
+    logdet_finish_kernel<<<1, 1024, 0, s>>>(w.tvec, m, 0, nullptr, w.sc, 1);
+  } else {
+    logdet_finish_kernel<<<1, 1024, 0, s>>>(w.pivots, m, 1, w.info, w.sc, 1);
+  }
+  IMB_LAUNCHED();
+  LikeScalars h;
+  IMB_TRY(read_scalars(w.sc, &h, s));
+  int* hi = static_cast<int*>(state().pinned);
+  IMB_CUDA(cudaMemcpyAsync(hi, w.info, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  IMB_CUDA(cudaStreamSynchronize(s));
+  if (!done && hi[0] != 0) {
+    if (out_info) { out_info[0] = bits; out_info[1] = hi[0]; }
+    return IMB_ESINGULAR;
+  }
+  if (h.sign < 0) bits |= IMB_INFO_NEGATIVE_DET;
+  *out_loglike = h.loglike;
+  if (out_info) { out_info[0] = bits; out_info[1] = lapack_info; }
+  return IMB_OK;
+}
+
+}  // namespace imb
+
+using namespace imb;
+
+extern "C" int imb_mcov(const double* sims, int N, int m, int estimator, double* out_mean,
+                        double* out_cov, double* out_rho, void* stream) {
+  IMB_TRY(check_init());
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!sims || !out_mean || !out_cov || N < 1 || m < 1) return IMB_EINVAL;
+  if (estimator < IMB_EST_EMPIRICAL || estimator > IMB_EST_DIAGONAL) return IMB_EINVAL;
+  const int slices = gram_slices(m);
+  IMB_TRY(ensure_workspace(256 * 8 + sizeof(LikeScalars) +
+                           sizeof(double) * ((size_t)m + (size_t)(slices + 1) * N * N)));
+  Carver c(state().ws);
+  LikeScalars* sc = c.take<LikeScalars>(1);
+  double* xvar = c.take<double>(m);
+  double* G = c.take<double>((size_t)N * N);
+  double* partial = c.take<double>((size_t)slices * N * N);
+  IMB_TRY(launch_colmean(sims, N, m, nullptr, out_mean, nullptr, s));
+  LikeScalars h;
+  h.rho = 0.0;
+  if (estimator == IMB_EST_DIAGONAL) {
+    IMB_TRY(launch_colvar(sims, N, m, xvar, s));
+    copy_cov_kernel<<<grid_blocks((long long)m * m, 256, 8), 256, 0, s>>>(nullptr, IMB_COV_NONE, m, xvar,
+                                                                       out_cov, m);
+    IMB_LAUNCHED();
+    IMB_CUDA(cudaStreamSynchronize(s));
+  } else {
+    IMB_TRY(launch_gram(sims, N, m, out_mean, nullptr, partial, G, s));
+    IMB_TRY(launch_oas_scalars(G, N, m, estimator, sc, s));
+    const int nt = (m + TB - 1) / TB;
+    build_cov_kernel<<<dim3(nt, nt), 256, 0, s>>>(sims, N, m, out_mean, sc, nullptr, IMB_COV_NONE, out_cov, m);
+    IMB_LAUNCHED();
+    IMB_TRY(read_scalars(sc, &h, s));
+  }
+  if (out_rho) *out_rho = h.rho;
+  return IMB_OK;
+}

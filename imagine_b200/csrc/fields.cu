@@ -1,0 +1,425 @@
+// Stage 1: grid-field evaluation (analytic models + Philox Gaussian components, fused with
+// the same-type sum), HEALPix RING directions, TestSimulator sampling.
+//
+// Reference arithmetic restated by oracle/fields.py; file:line citations in
+// include/imagine_b200.h.  HBM-write-bound streaming kernels: one thread owns a PAIR of
+// adjacent cells so that every Philox block (one Box-Muller pair) is consumed whole and
+// stores are 16/32-byte vectors, coalesced across the warp.
+#include "common.cuh"
+
+namespace imb {
+
+struct FieldArgs {
+  DevGrid g;
+  int nfields;
+  int rows;                 // 1 or n_real
+  int kind[IMB_MAX_FIELDS];
+  unsigned int stream[IMB_MAX_FIELDS];
+  double p[IMB_MAX_FIELDS][8];
+  const unsigned long long* seeds;  // device [n_real]
+};
+
+__device__ __forceinline__ void cell_xyz(const DevGrid& g, long long c, double& x, double& y,
+                                         double& z) {
+  const int iz = (int)(c % g.n[2]);
+  const long long t = c / g.n[2];
+  const int iy = (int)(t % g.n[1]);
+  const int ix = (int)(t / g.n[1]);
+  x = vertex_coord(g, 0, ix);
+  y = vertex_coord(g, 1, iy);
+  z = vertex_coord(g, 2, iz);
+}
+
+// ---- magnetic field: [rows, ncell, BS] ------------------------------------------------
+template <int BS, bool VEC>
+__global__ void __launch_bounds__(256) field_b_kernel(const __grid_constant__ FieldArgs a,
+                                                       double* __restrict__ out) {
+  const long long npair = (a.g.ncell + 1) >> 1;
+  const long long total = npair * a.rows;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
+       w += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(w / npair);
+    const long long q = w - (long long)r * npair;
+    double v[6];
+    bool first = true;
+    for (int f = 0; f < a.nfields; ++f) {
+      double t[6];
+      if (a.kind[f] == IMB_FIELD_CONST_B) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) t[k] = a.p[f][k % 3];
+      } else {  // IMB_FIELD_GAUSS_B: flat normal index n = 3*cell + comp, block n >> 1
+        const unsigned long long seed = a.seeds[r];
+        const double mu = a.p[f][0], sigma = a.p[f][1];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          double z0, z1;
+          philox_normal_pair(seed, a.stream[f], (unsigned long long)(3 * q + b), z0, z1);
+          t[2 * b] = __dadd_rn(__dmul_rn(z0, sigma), mu);
+          t[2 * b + 1] = __dadd_rn(__dmul_rn(z1, sigma), mu);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v[k] = first ? t[k] : __dadd_rn(v[k], t[k]);
+      first = false;
+    }
+    const long long c0 = 2 * q;
+    const bool has2 = (c0 + 1) < a.g.ncell;
+    double* o = out + ((long long)r * a.g.ncell + c0) * BS;
+    if (VEC && has2) {
+      if (BS == 3) {
+        double2* o2 = reinterpret_cast<double2*>(o);
+        o2[0] = make_double2(v[0], v[1]);
+        o2[1] = make_double2(v[2], v[3]);
+        o2[2] = make_double2(v[4], v[5]);
+      } else {
+        double4* o4 = reinterpret_cast<double4*>(o);
+        o4[0] = make_double4(v[0], v[1], v[2], 0.0);
+        o4[1] = make_double4(v[3], v[4], v[5], 0.0);
+      }
+    } else {
+      o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+      if (BS == 4) o[3] = 0.0;
+      if (has2) {
+        o[BS] = v[3]; o[BS + 1] = v[4]; o[BS + 2] = v[5];
+        if (BS == 4) o[BS + 3] = 0.0;
+      }
+    }
+  }
+}
+
+// ---- scalar fields (thermal electrons, cosmic-ray electrons): [rows, ncell] -----------
+__device__ __forceinline__ double scalar_model(const FieldArgs& a, int f, double x, double y,
+                                               double z) {
+  const double* p = a.p[f];
+  switch (a.kind[f]) {
+    case IMB_FIELD_CONST_NE:
+    case IMB_FIELD_CRE_CONST:
+      return p[0];
+    case IMB_FIELD_EXP_NE: {
+      const double R = sqrt(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+      return __dmul_rn(__dmul_rn(p[0], exp(-R / p[1])), exp(-fabs(z / p[2])));
+    }
+    case IMB_FIELD_COS_NE: {
+      const double fx = __dadd_rn(1.0, cos(__dadd_rn(__dmul_rn(p[1], x), p[2])));
+      const double fy = __dadd_rn(1.0, cos(__dadd_rn(__dmul_rn(p[3], y), p[4])));
+      const double fz = __dadd_rn(1.0, cos(__dadd_rn(__dmul_rn(p[5], z), p[6])));
+      return __dmul_rn(__dmul_rn(__dmul_rn(p[0], fx), fy), fz);
+    }
+    case IMB_FIELD_CRE_ANALYTIC: {
+      const double R = sqrt(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+      const double ch = cosh(z / p[2]);
+      return __dmul_rn(__dmul_rn(p[0], exp(-(R - p[3]) / p[1])), 1.0 / __dmul_rn(ch, ch));
+    }
+    default:
+      return 0.0;
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) field_scalar_kernel(const __grid_constant__ FieldArgs a,
+                                                            double* __restrict__ out) {
+  const long long npair = (a.g.ncell + 1) >> 1;
+  const long long total = npair * a.rows;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
+       w += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(w / npair);
+    const long long q = w - (long long)r * npair;
+    const long long c0 = 2 * q;
+    const bool has2 = (c0 + 1) < a.g.ncell;
+    double x0, y0, z0, x1 = 0, y1 = 0, z1 = 0;
+    cell_xyz(a.g, c0, x0, y0, z0);
+    if (has2) cell_xyz(a.g, c0 + 1, x1, y1, z1);
+    double v0 = 0, v1 = 0;
+    bool first = true;
+    for (int f = 0; f < a.nfields; ++f) {
+      double t0, t1;
+      if (a.kind[f] == IMB_FIELD_RANDOM_NE) {
+        double n0, n1;
+        philox_normal_pair(a.seeds[r], a.stream[f], (unsigned long long)q, n0, n1);
+        t0 = __dadd_rn(__dmul_rn(n0, a.p[f][1]), a.p[f][0]);
+        t1 = __dadd_rn(__dmul_rn(n1, a.p[f][1]), a.p[f][0]);
+        const double mn = a.p[f][2];
+        if (isfinite(mn)) {
+          if (t0 < mn) t0 = mn;
+          if (t1 < mn) t1 = mn;
+        }
+      } else {
+        t0 = scalar_model(a, f, x0, y0, z0);
+        t1 = has2 ? scalar_model(a, f, x1, y1, z1) : 0.0;
+      }
+      v0 = first ? t0 : __dadd_rn(v0, t0);
+      v1 = first ? t1 : __dadd_rn(v1, t1);
+      first = false;
+    }
+    double* o = out + (long long)r * a.g.ncell + c0;
+    if (VEC && has2) {
+      *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
+    } else {
+      o[0] = v0;
+      if (has2) o[1] = v1;
+    }
+  }
+}
+
+// ---- HEALPix RING pixel centres -> unit vectors (oracle/healpix.py) -------------------
+__global__ void healpix_ring_dirs_kernel(int nside, double* __restrict__ dirs) {
+  const long long npix = 12ll * nside * nside;
+  const long long ncap = 2ll * nside * (nside - 1);
+  const double pi = 3.141592653589793;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
+       p += (long long)gridDim.x * blockDim.x) {
+    double z, sth, phi;
+    if (p < ncap) {
+      long long i = (1 + (long long)floor(sqrt(1.0 + 2.0 * (double)p))) >> 1;
+      if (2 * i * (i - 1) > p) --i;
+      if (2 * (i + 1) * i <= p) ++i;
+      const long long j = p + 1 - 2 * i * (i - 1);
+      const double tmp = __dmul_rn((double)(i * i), 4.0 / (double)npix);
+      z = 1.0 - tmp;
+      sth = sqrt(__dmul_rn(tmp, 2.0 - tmp));
+      phi = __dmul_rn((double)j - 0.5, pi / (2.0 * (double)i));
+    } else if (p < npix - ncap) {
+      const long long q = p - ncap;
+      const long long i = q / (4 * nside) + nside;
+      const long long j = q % (4 * nside) + 1;
+      const double fodd = ((i + nside) & 1) ? 1.0 : 0.5;
+      z = __dmul_rn((double)(2 * nside - i), 2.0 / (3.0 * (double)nside));
+      sth = sqrt(__dmul_rn(1.0 - z, 1.0 + z));
+      phi = __dmul_rn((double)j - fodd, pi / (2.0 * (double)nside));
+    } else {
+      const long long q = npix - p;
+      long long i = (1 + (long long)floor(sqrt(2.0 * (double)q - 1.0))) >> 1;
+      if (2 * i * (i - 1) >= q) --i;
+      if (2 * (i + 1) * i < q) ++i;
+      const long long j = 4 * i + 1 - (q - 2 * i * (i - 1));
+      const double tmp = __dmul_rn((double)(i * i), 4.0 / (double)npix);
+      z = -(1.0 - tmp);
+      sth = sqrt(__dmul_rn(tmp, 2.0 - tmp));
+      phi = __dmul_rn((double)j - 0.5, pi / (2.0 * (double)i));
+    }
+    double s, c;
+    sincos(phi, &s, &c);
+    dirs[3 * p + 0] = __dmul_rn(sth, c);
+    dirs[3 * p + 1] = __dmul_rn(sth, s);
+    dirs[3 * p + 2] = z;
+  }
+}
+
+// ---- TestSimulator: nearest-vertex sampling of B[axis]*ne ---------------------------------
+__device__ __forceinline__ int nearest_vertex(const DevGrid& g, int axis, double p, int* oob) {
+  const int n = g.n[axis];
+  const double c_first = g.lo[axis];
+  const double c_last = vertex_coord(g, axis, n - 1);
+  if (!(p >= c_first) || !(p <= c_last)) {  // also catches NaN
+    *oob = 1;
+    return 0;
+  }
+  if (n == 1) return 0;
+  // i = searchsorted(c, p, 'right') - 1 clipped to [0, n-2], on the exact vertex values
+  int i = (int)floor((p - g.lo[axis]) * g.inv_step[axis]);
+  i = max(0, min(i, n - 2));
+  while (i > 0 && vertex_coord(g, axis, i) > p) --i;
+  while (i < n - 2 && vertex_coord(g, axis, i + 1) <= p) ++i;
+  const double ci = vertex_coord(g, axis, i), cn = vertex_coord(g, axis, i + 1);
+  const double yi = __ddiv_rn(__dsub_rn(p, ci), __dsub_rn(cn, ci));
+  return yi <= 0.5 ? i : i + 1;
+}
+
+__global__ void test_simulate_kernel(DevGrid g, const double* __restrict__ B, int rows_B, int bs,
+                                     const double* __restrict__ ne, int rows_ne, int n_real,
+                                     int b_axis, const double* __restrict__ pts, int P,
+                                     double scale, double* __restrict__ out, int* oob_flag) {
+  const long long total = (long long)n_real * P;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
+       w += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(w / P), p = (int)(w % P);
+    int oob = 0;
+    const int ix = nearest_vertex(g, 0, pts[3 * p + 0], &oob);
+    const int iy = nearest_vertex(g, 1, pts[3 * p + 1], &oob);
+    const int iz = nearest_vertex(g, 2, pts[3 * p + 2], &oob);
+    if (oob) {
+      atomicOr(oob_flag, 1);
+      out[w] = nan("");
+      continue;
+    }
+    const long long c = ((long long)ix * g.n[1] + iy) * g.n[2] + iz;
+    const double b = B[((long long)(rows_B > 1 ? r : 0) * g.ncell + c) * bs + b_axis];
+    const double e = ne[(long long)(rows_ne > 1 ? r : 0) * g.ncell + c];
+    out[w] = __dmul_rn(__dmul_rn(b, e), scale);
+  }
+}
+
+__global__ void pol_derive_kernel(const double* __restrict__ Q, const double* __restrict__ U,
+                                  long long n, double* __restrict__ PI, double* __restrict__ PA) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double q = Q[i], u = U[i];
+    if (PI) PI[i] = sqrt(__dadd_rn(__dmul_rn(q, q), __dmul_rn(u, u)));
+    if (PA) PA[i] = 0.5 * atan2(u, q);
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------
+int make_dev_grid(const imb_grid* grid, DevGrid* g) {
+  if (!grid) return IMB_EINVAL;
+  g->ncell = 1;
+  for (int a = 0; a < 3; ++a) {
+    if (grid->n[a] < 1) return IMB_EINVAL;
+    g->n[a] = grid->n[a];
+    g->lo[a] = grid->lo[a];
+    const double span = grid->hi[a] - grid->lo[a];
+    g->step[a] = grid->n[a] != 1 ? span / (double)(grid->n[a] - 1) : 1.0;
+    g->inv_step[a] = (grid->n[a] != 1 && span != 0.0) ? (double)(grid->n[a] - 1) / span : 0.0;
+    g->ncell *= grid->n[a];
+  }
+  return IMB_OK;
+}
+
+static int field_type(int kind) {
+  switch (kind) {
+    case IMB_FIELD_CONST_B: case IMB_FIELD_GAUSS_B: return 0;
+    case IMB_FIELD_CONST_NE: case IMB_FIELD_EXP_NE: case IMB_FIELD_COS_NE:
+    case IMB_FIELD_RANDOM_NE: return 1;
+    case IMB_FIELD_CRE_ANALYTIC: case IMB_FIELD_CRE_CONST: return 2;
+    default: return -1;
+  }
+}
+static bool is_stochastic(int kind) {
+  return kind == IMB_FIELD_GAUSS_B || kind == IMB_FIELD_RANDOM_NE;
+}
+
+int grid_blocks(long long work, int threads, int per_sm) {
+  const long long need = (work + threads - 1) / threads;
+  const long long cap = (long long)state().sm_count * per_sm;
+  return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+}  // namespace imb
+
+using namespace imb;
+
+extern "C" {
+
+int imb_field_rows(const imb_field_desc* fields, int nfields, int type, int n_real) {
+  int rows = 0;
+  for (int f = 0; f < nfields; ++f) {
+    if (field_type(fields[f].kind) != type) continue;
+    if (is_stochastic(fields[f].kind)) return n_real;
+    rows = 1;
+  }
+  return rows;
+}
+
+int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfields,
+                   const uint64_t* seeds, int n_real, double* out_B, int rows_B, int b_stride,
+                   double* out_ne, int rows_ne, double* out_cre, int rows_cre, void* stream_) {
+  IMB_TRY(check_init());
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DevGrid g;
+  IMB_TRY(make_dev_grid(grid, &g));
+  if (!fields || nfields < 0 || n_real < 1) return IMB_EINVAL;
+  if (out_B && b_stride != 3 && b_stride != 4) return IMB_EINVAL;
+  for (int f = 0; f < nfields; ++f)
+    if (field_type(fields[f].kind) < 0) return IMB_EINVAL;
+
+  // seeds -> device scratch (pageable H2D is staged before the call returns)
+  IMB_TRY(ensure_workspace(sizeof(unsigned long long) * (size_t)n_real + 256));
+  unsigned long long* d_seeds = static_cast<unsigned long long*>(state().ws);
+  bool any_stochastic = false;
+  for (int f = 0; f < nfields; ++f) any_stochastic |= is_stochastic(fields[f].kind);
+  if (any_stochastic) {
+    if (!seeds) return IMB_EINVAL;
+    IMB_CUDA(cudaMemcpyAsync(d_seeds, seeds, sizeof(unsigned long long) * (size_t)n_real,
+                             cudaMemcpyHostToDevice, stream));
+  }
+
+  double* outs[3] = {out_B, out_ne, out_cre};
+  const int rows[3] = {rows_B, rows_ne, rows_cre};
+  for (int type = 0; type < 3; ++type) {
+    if (!outs[type]) continue;
+    const int need = imb_field_rows(fields, nfields, type, n_real);
+    if (need == 0) return IMB_EINVAL;               // output requested, no field of that type
+    if (rows[type] != need) return IMB_EINVAL;
+    FieldArgs a;
+    a.g = g;
+    a.rows = need;
+    a.seeds = d_seeds;
+    a.nfields = 0;
+    for (int f = 0; f < nfields; ++f) {
+      if (field_type(fields[f].kind) != type) continue;
+      if (a.nfields == IMB_MAX_FIELDS) return IMB_EUNSUPPORTED;
+      a.kind[a.nfields] = fields[f].kind;
+      a.stream[a.nfields] = (unsigned int)fields[f].stream;
+      for (int k = 0; k < 8; ++k) a.p[a.nfields][k] = fields[f].p[k];
+      a.nfields++;
+    }
+    const long long work = ((g.ncell + 1) / 2) * need;
+    const int blocks = grid_blocks(work, 256, 8);
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(outs[type]);
+    if (type == 0) {
+      const long long row_elems = g.ncell * b_stride;
+      if (b_stride == 3) {
+        const bool vec = (addr % 16 == 0) && (need == 1 || row_elems % 2 == 0);
+        if (vec) field_b_kernel<3, true><<<blocks, 256, 0, stream>>>(a, outs[type]);
+        else field_b_kernel<3, false><<<blocks, 256, 0, stream>>>(a, outs[type]);
+      } else {
+        const bool vec = (addr % 32 == 0);
+        if (vec) field_b_kernel<4, true><<<blocks, 256, 0, stream>>>(a, outs[type]);
+        else field_b_kernel<4, false><<<blocks, 256, 0, stream>>>(a, outs[type]);
+      }
+    } else {
+      const bool vec = (addr % 16 == 0) && (need == 1 || g.ncell % 2 == 0);
+      if (vec) field_scalar_kernel<true><<<blocks, 256, 0, stream>>>(a, outs[type]);
+      else field_scalar_kernel<false><<<blocks, 256, 0, stream>>>(a, outs[type]);
+    }
+    IMB_LAUNCHED();
+  }
+  return IMB_OK;
+}
+
+int imb_healpix_ring_dirs(int nside, double* dirs, void* stream) {
+  IMB_TRY(check_init());
+  if (nside < 1 || nside > 8192 || !dirs) return IMB_EINVAL;
+  const long long npix = 12ll * nside * nside;
+  healpix_ring_dirs_kernel<<<grid_blocks(npix, 256, 8), 256, 0, (cudaStream_t)stream>>>(nside, dirs);
+  IMB_LAUNCHED();
+  return IMB_OK;
+}
+
+int imb_test_simulate(const imb_grid* grid, const double* B, int rows_B, int b_stride,
+                      const double* ne, int rows_ne, int n_real, int b_axis,
+                      const double* points, int n_points, double scale, double* out,
+                      void* stream_) {
+  IMB_TRY(check_init());
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DevGrid g;
+  IMB_TRY(make_dev_grid(grid, &g));
+  if (!B || !ne || !points || !out || n_points < 0 || n_real < 1) return IMB_EINVAL;
+  if (b_axis < 0 || b_axis > 2 || (b_stride != 3 && b_stride != 4)) return IMB_EINVAL;
+  if ((rows_B != 1 && rows_B != n_real) || (rows_ne != 1 && rows_ne != n_real)) return IMB_EINVAL;
+  if (n_points == 0) return IMB_OK;
+  IMB_TRY(ensure_workspace(256));
+  int* flag = static_cast<int*>(state().ws);
+  IMB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
+  const long long work = (long long)n_real * n_points;
+  test_simulate_kernel<<<grid_blocks(work, 128, 16), 128, 0, stream>>>(
+      g, B, rows_B, b_stride, ne, rows_ne, n_real, b_axis, points, n_points, scale, out, flag);
+  IMB_LAUNCHED();
+  int* h = static_cast<int*>(state().pinned);
+  IMB_CUDA(cudaMemcpyAsync(h, flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  IMB_CUDA(cudaStreamSynchronize(stream));
+  return *h ? IMB_EBOUNDS : IMB_OK;
+}
+
+int imb_pol_derive(const double* Q, const double* U, int64_t count, double* out_PI,
+                   double* out_PA, void* stream) {
+  IMB_TRY(check_init());
+  if (!Q || !U || count < 0) return IMB_EINVAL;
+  if (count == 0) return IMB_OK;
+  pol_derive_kernel<<<grid_blocks(count, 256, 8), 256, 0, (cudaStream_t)stream>>>(Q, U, count,
+                                                                               out_PI, out_PA);
+  IMB_LAUNCHED();
+  return IMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+"""
+Tensor-level Python face of the C ABI: torch tensors in (device buffers only), torch tensors
+or floats out.  Every function here is a thin argument marshaller around one `imb_*` entry
+point; the arithmetic lives in csrc/*.cu.  No CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .constants import sync_coefficient
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _f64(t, name):
+    torch = _torch()
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64):
+        raise TypeError('%s must be a CUDA float64 tensor' % name)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class DeviceGrid:
+    """UniformGrid geometry (fields/grid.py:189-275), cartesian, canonical units (kpc)."""
+
+    def __init__(self, box, resolution):
+        self.box = np.asarray(box, dtype=np.float64).reshape(3, 2)
+        self.resolution = np.asarray(resolution, dtype=np.int64).reshape(3)
+        self.c = L.make_grid(self.box, self.resolution)
+
+    @property
+    def shape(self):
+        return tuple(int(n) for n in self.resolution)
+
+    @property
+    def ncell(self):
+        return int(np.prod(self.resolution))
+
+
+class LosSettings:
+    """Observer geometry + radial sampling + synchrotron spectrum (imb_los_cfg)."""
+
+    def __init__(self, observer=(-8.3, 0.0, 0.006), dr=0.1, r_max=30.0, n_steps=None,
+                 nu_ghz=23.0, alpha=3.0, beta=0.0, theta=0.0, e0_gev=20.6):
+        self.observer = tuple(float(v) for v in observer)
+        self.dr = float(dr)
+        self.n_steps = int(n_steps) if n_steps is not None else int(np.ceil(r_max / dr - 1e-9))
+        self.nu_ghz, self.alpha, self.beta, self.theta, self.e0_gev = (
+            float(nu_ghz), float(alpha), float(beta), float(theta), float(e0_gev))
+
+    def with_frequency(self, nu_ghz):
+        return LosSettings(self.observer, self.dr, None, self.n_steps, nu_ghz, self.alpha,
+                           self.beta, self.theta, self.e0_gev)
+
+    def c_struct(self):
+        cfg = L.LosCfg()
+        for a in range(3):
+            cfg.observer[a] = self.observer[a]
+        cfg.dr, cfg.n_steps, cfg.nu_ghz = self.dr, self.n_steps, self.nu_ghz
+        cfg.alpha, cfg.beta, cfg.theta, cfg.e0_gev = self.alpha, self.beta, self.theta, self.e0_gev
+        cfg.sync_k = sync_coefficient(self.alpha, self.nu_ghz, self.e0_gev)
+        return cfg
+
+
+# --------------------------------------------------------------------------------- stage 1
+def field_rows(descs, n_real):
+    arr, n = L.make_field_descs(descs)
+    lib = L.load()
+    return tuple(lib.imb_field_rows(arr, n, t, n_real) for t in range(3))
+
+
+def field_eval(grid, descs, seeds, n_real=None, b_stride=4, out=None):
+    """
+    Evaluate and sum all fields (imb_field_eval).  Returns dict with any of
+    'magnetic_field' [rows, ncell, b_stride], 'thermal_electron_density' [rows, ncell],
+    'cosmic_ray_electron_density' [rows, ncell]; rows is n_real when a stochastic field of the
+    type is present and 1 otherwise.
+    """
+    torch = _torch()
+    dev = L.init()
+    seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64).reshape(-1))
+    if n_real is None:
+        n_real = int(seeds.size)
+    if seeds.size != n_real:
+        raise ValueError('need one seed per realisation')
+    arr, n = L.make_field_descs(descs)
+    rows = field_rows(descs, n_real)
+    names = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
+    bufs = {}
+    for t, name in enumerate(names):
+        if rows[t] == 0:
+            continue
+        shape = (rows[t], grid.ncell, b_stride) if t == 0 else (rows[t], grid.ncell)
+        if out is not None and name in out:
+            buf = out[name]
+            if tuple(buf.shape) != shape:
+                raise ValueError('preallocated %s has shape %s, need %s' % (name, tuple(buf.shape), shape))
+        else:
+            buf = torch.empty(shape, dtype=torch.float64, device='cuda:%d' % dev)
+        bufs[name] = buf
+    B, ne, cre = (bufs.get(k) for k in names)
+    L.check(L.load().imb_field_eval(
+        C.byref(grid.c), arr, n, seeds.ctypes.data_as(C.c_void_p), n_real,
+        L.ptr(B), rows[0], b_stride, L.ptr(ne), rows[1], L.ptr(cre), rows[2], L.stream_ptr()))
+    return bufs
+
+
+def test_simulate(grid, B, ne, n_real, points, b_axis=1, scale=1.0):
+    """TestSimulator.simulate for all realisations: [n_real, P] (imb_test_simulate)."""
+    torch = _torch()
+    L.init()
+    B, ne = _f64(B, 'B'), _f64(ne, 'ne')
+    pts = _f64(points, 'points').reshape(-1, 3)
+    out = torch.empty((n_real, pts.shape[0]), dtype=torch.float64, device=B.device)
+    L.check(L.load().imb_test_simulate(
+        C.byref(grid.c), L.ptr(B), B.shape[0], B.shape[-1], L.ptr(ne), ne.shape[0], n_real,
+        int(b_axis), L.ptr(pts), pts.shape[0], float(scale), L.ptr(out), L.stream_ptr()))
+    return out
+
+
+# --------------------------------------------------------------------------------- stage 2
+def healpix_ring_dirs(nside):
+    torch = _torch()
+    dev = L.init()
+    out = torch.empty((12 * int(nside) ** 2, 3), dtype=torch.float64, device='cuda:%d' % dev)
+    L.check(L.load().imb_healpix_ring_dirs(int(nside), L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def los_integrate(grid, settings, dirs, B, ne=None, cre=None, n_real=1,
+                  want=('dm', 'fd', 'I', 'Q', 'U'), out=None):
+    """
+    Integrate every realisation along `dirs` [m,3] (imb_los_integrate).  Returns a dict of
+    [n_real, m] tensors for the requested quantities.
+    """
+    torch = _torch()
+    L.init()
+    dirs = _f64(dirs, 'dirs').reshape(-1, 3)
+    m = dirs.shape[0]
+    B = _f64(B, 'B')
+    ne = None if ne is None else _f64(ne, 'ne')
+    cre = None if cre is None else _f64(cre, 'cre')
+    res = {}
+    for k in ('dm', 'fd', 'I', 'Q', 'U'):
+        if k in want:
+            if out is not None and k in out:
+                res[k] = out[k]
+            else:
+                res[k] = torch.empty((n_real, m), dtype=torch.float64, device=B.device)
+    cfg = settings.c_struct()
+    L.check(L.load().imb_los_integrate(
+        C.byref(grid.c), C.byref(cfg), L.ptr(dirs), m, L.ptr(B), B.shape[0], B.shape[-1],
+        L.ptr(ne), 0 if ne is None else ne.shape[0], L.ptr(cre), 0 if cre is None else cre.shape[0],
+        n_real, L.ptr(res.get('dm')), L.ptr(res.get('fd')), L.ptr(res.get('I')),
+        L.ptr(res.get('Q')), L.ptr(res.get('U')), L.stream_ptr()))
+    return res
+
+
+def pol_derive(Q, U, want_pi=True, want_pa=True):
+    torch = _torch()
+    L.init()
+    Q, U = _f64(Q, 'Q'), _f64(U, 'U')
+    PI = torch.empty_like(Q) if want_pi else None
+    PA = torch.empty_like(Q) if want_pa else None
+    L.check(L.load().imb_pol_derive(L.ptr(Q), L.ptr(U), Q.numel(), L.ptr(PI), L.ptr(PA),
+                                    L.stream_ptr()))
+    return PI, PA
+
+
+# --------------------------------------------------------------------------------- stage 3
+def ensemble_mean(sims):
+    torch = _torch()
+    L.init()
+    sims = _f64(sims, 'sims')
+    N, m = sims.shape
+    out = torch.empty((1, m), dtype=torch.float64, device=sims.device)
+    L.check(L.load().imb_ensemble_mean(L.ptr(sims), N, m, L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def ensemble_var(sims):
+    torch = _torch()
+    L.init()
+    sims = _f64(sims, 'sims')
+    N, m = sims.shape
+    out = torch.empty((m,), dtype=torch.float64, device=sims.device)
+    L.check(L.load().imb_ensemble_var(L.ptr(sims), N, m, L.ptr(out), L.stream_ptr()))
+    return out
+
+
+_EST = {'empirical': L.EST_EMPIRICAL, 'oas': L.EST_OAS, 'diagonal': L.EST_DIAGONAL}
+_ROUTE = {'auto': L.ROUTE_AUTO, 'gram': L.ROUTE_GRAM, 'dense': L.ROUTE_DENSE}
+
+
+def mcov(sims, estimator='oas'):
+    """(mean [1,m], cov [m,m], rho) = empirical_mcov / oas_mcov / diagonal_mcov on device."""
+    torch = _torch()
+    L.init()
+    sims = _f64(sims, 'sims')
+    N, m = sims.shape
+    mean = torch.empty((1, m), dtype=torch.float64, device=sims.device)
+    cov = torch.empty((m, m), dtype=torch.float64, device=sims.device)
+    rho = C.c_double(0.0)
+    L.check(L.load().imb_mcov(L.ptr(sims), N, m, _EST[estimator], L.ptr(mean), L.ptr(cov),
+                              C.byref(rho), L.stream_ptr()))
+    return mean, cov, rho.value
+
+
+def _cov_kind(cov):
+    if cov is None:
+        return L.COV_NONE
+    if cov.dim() == 1:
+        return L.COV_VARIANCE
+    if cov.dim() == 2 and cov.shape[0] == cov.shape[1]:
+        return L.COV_DENSE
+    raise ValueError('covariance must be [m] (variance) or [m,m]')
+
+
+def loglike_ensemble(sims, meas, cov, estimator='oas', route='auto',
+                     use_trace_approximation=False, return_info=False):
+    L.init()
+    sims, meas, cov = _f64(sims, 'sims'), _f64(meas, 'meas').reshape(-1), _f64(cov, 'cov')
+    N, m = sims.shape
+    if meas.numel() != m or cov.shape[0] != m:
+        raise ValueError('shape mismatch between simulations, measurements and covariance')
+    out, info = C.c_double(0.0), (C.c_int32 * 2)()
+    L.check(L.load().imb_loglike_ensemble(
+        L.ptr(sims), N, m, L.ptr(meas), L.ptr(cov), _cov_kind(cov), _EST[estimator], _ROUTE[route],
+        int(bool(use_trace_approximation)), C.byref(out), info, L.stream_ptr()))
+    return (out.value, (info[0], info[1])) if return_info else out.value
+
+
+def loglike_ensemble_diagonal(sims, meas, var):
+    L.init()
+    sims, meas, var = _f64(sims, 'sims'), _f64(meas, 'meas').reshape(-1), _f64(var, 'var')
+    N, m = sims.shape
+    if meas.numel() != m or var.numel() != m:
+        raise ValueError('shape mismatch between simulations, measurements and variance')
+    out = C.c_double(0.0)
+    L.check(L.load().imb_loglike_ensemble_diagonal(L.ptr(sims), N, m, L.ptr(meas), L.ptr(var),
+                                                   C.byref(out), L.stream_ptr()))
+    return out.value
+
+
+def loglike_simple(sims, meas, cov=None, return_info=False):
+    L.init()
+    sims, meas = _f64(sims, 'sims'), _f64(meas, 'meas').reshape(-1)
+    cov = None if cov is None else _f64(cov, 'cov')
+    N, m = sims.shape
+    if meas.numel() != m or (cov is not None and cov.shape[0] != m):
+        raise ValueError('shape mismatch between simulations, measurements and covariance')
+    out, info = C.c_double(0.0), (C.c_int32 * 2)()
+    L.check(L.load().imb_loglike_simple(L.ptr(sims), N, m, L.ptr(meas), L.ptr(cov), _cov_kind(cov),
+                                        C.byref(out), info, L.stream_ptr()))
+    return (out.value, (info[0], info[1])) if return_info else out.value
+
+
+def gather_columns(x, idx):
+    """mask_obs / mask_var on device: x[:, idx]."""
+    torch = _torch()
+    L.init()
+    x = _f64(x, 'x')
+    squeeze = x.dim() == 1
+    x2 = x.reshape(1, -1) if squeeze else x
+    out = torch.empty((x2.shape[0], idx.numel()), dtype=torch.float64, device=x.device)
+    L.check(L.load().imb_gather_columns(L.ptr(x2), x2.shape[0], x2.shape[1], L.ptr(idx), idx.numel(),
+                                        L.ptr(out), L.stream_ptr()))
+    return out.reshape(-1) if squeeze else out
+
+
+def gather_cov(cov, idx):
+    """mask_cov on device: cov[idx][:, idx]."""
+    torch = _torch()
+    L.init()
+    cov = _f64(cov, 'cov')
+    out = torch.empty((idx.numel(), idx.numel()), dtype=torch.float64, device=cov.device)
+    L.check(L.load().imb_gather_cov(L.ptr(cov), cov.shape[0], L.ptr(idx), idx.numel(), L.ptr(out),
+                                    L.stream_ptr()))
+    return out

@@ -1,0 +1,193 @@
+"""GPU parity, stage 3: ensemble statistics and log-likelihoods vs the reference goldens / oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import likelihood as OK                      # noqa: E402
+from tests.helpers import GOLDEN_DIR, load_golden_cases   # noqa: E402
+
+CASES = load_golden_cases()
+
+
+@pytest.fixture(scope='module')
+def eng():
+    import torch
+    assert torch.cuda.is_available()
+    from imagine_b200 import engine, _lib
+    _lib.init(0)
+    return engine
+
+
+def _dev(a):
+    import torch
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def _gpu_value(eng, case, route='auto'):
+    import torch
+    sims, meas, cov = _dev(case['sims']), _dev(case['meas']), _dev(case['cov'])
+    if case['mask'] is not None:
+        idx = torch.from_numpy(np.flatnonzero(case['mask']).astype(np.int32)).cuda()
+        sims, meas = eng.gather_columns(sims, idx), eng.gather_columns(meas, idx)
+        if cov is not None:
+            cov = eng.gather_columns(cov, idx) if cov.dim() == 1 else eng.gather_cov(cov, idx)
+    if case['kind'] == 'ensemble':
+        return eng.loglike_ensemble(sims, meas, cov, estimator=str(case['estimator']), route=route,
+                                    use_trace_approximation=bool(case['use_trace_approximation']),
+                                    return_info=True)
+    if case['kind'] == 'ensemble_diagonal':
+        var = cov if cov.dim() == 1 else cov.diagonal().contiguous()
+        return eng.loglike_ensemble_diagonal(sims, meas, var), (0, 0)
+    return eng.loglike_simple(sims, meas, cov, return_info=True)
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_golden_cases(eng, name):
+    """north_star: log-likelihoods within 1e-8 absolute of the reference path."""
+    got, info = _gpu_value(eng, CASES[name])
+    assert abs(got - CASES[name]['value']) <= 1e-8, (got, CASES[name]['value'], info)
+
+
+@pytest.mark.parametrize('name', [n for n, c in CASES.items()
+                                  if c['kind'] == 'ensemble' and c['estimator'] != 'diagonal'
+                                  and not c['use_trace_approximation']])
+def test_dense_route_on_every_ensemble_case(eng, name):
+    got, info = _gpu_value(eng, CASES[name], route='dense')
+    assert info[0] & 2
+    assert abs(got - CASES[name]['value']) <= 1e-8, (got, CASES[name]['value'], info)
+
+
+def test_route_selection_and_factorisation_flags(eng):
+    _, info = _gpu_value(eng, CASES['ens_oas_var'])
+    assert info[0] & 1                                   # gram
+    _, info = _gpu_value(eng, CASES['ens_oas_dense_spd'])
+    assert (info[0] & 2) and (info[0] & 4)               # dense + Cholesky
+    _, info = _gpu_value(eng, CASES['ens_oas_dense_nonspd'])
+    assert (info[0] & 2) and (info[0] & 8)               # dense + LU (non-symmetric input)
+
+
+def test_ensemble_equals_simple_exactly_for_identical_rows(eng):
+    """tests/test_likelihood.py:81-149 asserts `==`, with and without the trace approximation."""
+    e, _ = _gpu_value(eng, CASES['ens_identical_nonspd4'])
+    s, _ = _gpu_value(eng, CASES['simple_identical_nonspd4'])
+    assert e == s
+    e, _ = _gpu_value(eng, CASES['ens_identical_trace4'])
+    s, _ = _gpu_value(eng, CASES['simple_identical_diag4'])
+    assert e == s
+    rng = np.random.default_rng(0)           # the reference test itself, many draws
+    for m in (4, 8, 48):
+        for _ in range(5):
+            row = rng.random((1, m))
+            case = dict(kind='ensemble', sims=np.repeat(row, 2, 0), meas=rng.random(m), cov=rng.random((m, m)),
+                        mask=None, estimator='oas', use_trace_approximation=False)
+            e, _ = _gpu_value(eng, case)
+            s, _ = _gpu_value(eng, dict(case, kind='simple'))
+            assert e == s
+            assert abs(e - OK.simple_loglike(case['sims'], case['meas'], case['cov'])) <= 1e-8 * max(1, abs(e))
+
+
+def test_diagonal_estimator_equals_ensemble_diagonal(eng):
+    """tests/test_likelihood.py:151-178."""
+    a, _ = _gpu_value(eng, CASES['ens_diagfunc_var'])
+    b, _ = _gpu_value(eng, CASES['ensdiag_var'])
+    assert np.allclose(a, b)
+
+
+def test_mean_var_bit_exact(eng):
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(13, 1000))
+    assert np.array_equal(eng.ensemble_mean(_dev(x)).cpu().numpy(), np.mean(x, axis=0).reshape(1, -1))
+    assert np.array_equal(eng.ensemble_var(_dev(x)).cpu().numpy(), x.var(axis=0))
+
+
+@pytest.mark.parametrize('est', ['oas', 'empirical', 'diagonal'])
+def test_mcov_matches_oracle(eng, est):
+    z = np.load(GOLDEN_DIR + '/estimator_golden.npz')
+    mean, cov, rho = eng.mcov(_dev(z['x']), est)
+    omean, ocov = OK.ESTIMATORS[est](z['x'])
+    assert np.array_equal(mean.cpu().numpy(), omean)
+    assert np.allclose(cov.cpu().numpy(), ocov, rtol=1e-12, atol=1e-15)
+    if est == 'oas':
+        assert np.allclose(cov.cpu().numpy(), z['oas_cov'], rtol=1e-12, atol=1e-15)   # reference's own output
+
+
+def test_single_row_ensemble_zero_covariance(eng):
+    """tests/test_tools.py:154-184."""
+    x = np.random.default_rng(3).random((1, 32))
+    for est in ('oas', 'empirical'):
+        mean, cov, _ = eng.mcov(_dev(x), est)
+        assert np.array_equal(mean.cpu().numpy(), x)
+        assert np.all(cov.cpu().numpy() == 0.0)
+
+
+@pytest.mark.parametrize('N,m', [(16, 3072), (64, 12288), (3, 1000), (200, 517), (64, 49152)])
+def test_gram_route_at_scale_vs_oracle_gram(eng, N, m):
+    """Sizes where the dense oracle is too slow: compare with the O(mN^2) NumPy restatement."""
+    rng = np.random.default_rng(N * m)
+    base = 30 * rng.normal(size=m)
+    sims = base + 8 * rng.normal(size=(N, m))
+    meas = base + 8 * rng.normal(size=m)
+    var = rng.uniform(0.05, 0.2, size=m)
+    for est in ('oas', 'empirical'):
+        got = eng.loglike_ensemble(_dev(sims), _dev(meas), _dev(var), estimator=est)
+        want = OK.ensemble_loglike_gram(sims, meas, var, estimator=est)
+        assert abs(got - want) <= 1e-8 * max(1.0, abs(want) * 1e-4), (got, want)
+
+
+@pytest.mark.parametrize('N,m', [(16, 768), (8, 1500)])
+def test_dense_vs_gram_vs_reference_algebra(eng, N, m):
+    """Dense DMMA + Cholesky route == Gram route == NumPy dense LU (the reference algebra)."""
+    rng = np.random.default_rng(m)
+    sims = rng.normal(size=(N, m)) * 3 + rng.normal(size=m)
+    meas = rng.normal(size=m)
+    var = rng.uniform(0.5, 1.5, size=m)
+    want = OK.ensemble_loglike(sims, meas, var)
+    g = eng.loglike_ensemble(_dev(sims), _dev(meas), _dev(var), route='gram')
+    d, info = eng.loglike_ensemble(_dev(sims), _dev(meas), _dev(var), route='dense', return_info=True)
+    assert info[0] & 4
+    assert abs(g - want) <= 1e-8 and abs(d - want) <= 1e-8, (g, d, want)
+    a = rng.normal(size=(m, m))
+    dense = a @ a.T / m + np.eye(m)
+    want = OK.ensemble_loglike(sims, meas, dense)
+    d = eng.loglike_ensemble(_dev(sims), _dev(meas), _dev(dense))
+    assert abs(d - want) <= 1e-8, (d, want)
+    s = eng.loglike_simple(_dev(sims), _dev(meas), _dev(dense))
+    assert abs(s - OK.simple_loglike(sims, meas, dense)) <= 1e-8
+
+
+def test_lu_fallback_medium_nonsymmetric(eng):
+    rng = np.random.default_rng(9)
+    m, N = 200, 6
+    sims, meas = rng.normal(size=(N, m)), rng.normal(size=m)
+    cov = rng.random((m, m)) + 5 * np.eye(m)
+    got, info = eng.loglike_ensemble(_dev(sims), _dev(meas), _dev(cov), return_info=True)
+    assert info[0] & 8
+    want = OK.ensemble_loglike(sims, meas, cov)
+    assert abs(got - want) <= 1e-8 * max(1, abs(want))
+
+
+def test_symmetric_indefinite_falls_back_to_lu(eng):
+    rng = np.random.default_rng(10)
+    m, N = 24, 4
+    sims, meas = rng.normal(size=(N, m)), rng.normal(size=m)
+    a = rng.normal(size=(m, m))
+    cov = a + a.T                                        # symmetric, indefinite
+    got, info = eng.loglike_simple(_dev(sims), _dev(meas), _dev(cov), return_info=True)
+    assert info[0] & 8 and info[1] > 0
+    want = OK.simple_loglike(sims, meas, cov)
+    assert abs(got - want) <= 1e-8 * max(1, abs(want))
+
+
+def test_singular_matrix_raises(eng):
+    m = 6
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.loglike_simple(_dev(np.ones((2, m))), _dev(np.zeros(m)), _dev(np.zeros((m, m))))
+
+
+def test_shape_errors(eng):
+    with pytest.raises(ValueError):
+        eng.loglike_ensemble(_dev(np.ones((2, 5))), _dev(np.ones(4)), _dev(np.ones(5)))
+    with pytest.raises(ValueError):
+        eng.loglike_ensemble(_dev(np.ones((2, 5))), _dev(np.ones(5)), _dev(np.ones(5)), estimator='diagonal',
+                             route='gram')
