@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""
+bench.py -- ensemble log-likelihood evaluations per second (BASELINE.json metric).
+
+A "step" is ONE full ensemble log-likelihood evaluation at one parameter point:
+  fields (N realisations on the grid) -> LOS maps (K observables x N x 12 Nside^2)
+  -> sum over observables of the EnsembleLikelihood term (OAS covariance).
+Default workload = BASELINE.json configs[2] ("c3"): 128^3 grid, Nside 64, 64 realisations,
+RM + DM + synchrotron I/Q/U at 23 GHz, OAS covariance, diagonal measurement covariance.
+With N GPUs the ensemble is sharded (N/P realisations per rank, strong scaling) and the maps are
+exchanged with one NCCL all-gather per observable.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same metric
+through the plugin API with host buffers (H2D of seeds/measurements, D2H of the result inside
+the timed region).  `--impl reference` times the CPU path (oracle/cpu_path.py) instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: grid G, nside, realisations, observables
+    'c2': dict(G=64, nside=32, n_real=16, quantities=('fd',)),
+    'c3': dict(G=128, nside=64, n_real=64, quantities=('fd', 'dm', 'I', 'Q', 'U')),
+    'c4': dict(G=256, nside=128, n_real=256, quantities=('fd', 'dm', 'I', 'Q', 'U')),
+}
+BOX = [[-20.0, 20.0], [-20.0, 20.0], [-4.0, 4.0]]          # tests/data/test_ham.xml:38-43
+LOS_KW = dict(observer=(-8.3, 0.0, 0.006), dr=0.1, r_max=30.0, nu_ghz=23.0, alpha=3.0,
+              beta=0.0, theta=0.0, e0_gev=20.6)
+# field kinds (include/imagine_b200.h)
+CONST_B, GAUSS_B, CONST_NE, EXP_NE, COS_NE, RANDOM_NE, CRE_ANALYTIC, CRE_CONST = range(8)
+
+
+def field_descs(quantities):
+    descs = [(EXP_NE, [0.01, 3.0, 0.1], 0), (CONST_B, [0.0, 1.0, 0.0], 1), (GAUSS_B, [0.0, 2.0], 2)]
+    if any(q in quantities for q in 'IQU'):
+        descs.append((CRE_ANALYTIC, [0.0217, 5.0, 1.0, 8.3], 3))
+    return descs
+
+
+def ensemble_seeds(n):
+    # pipelines/pipeline.py:805-813 with master_seed = 1 (tools/config.py:54)
+    np.random.seed(1)
+    return np.random.randint(1, 1431655765, n).astype(np.uint64)
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured'
+    except Exception:
+        return 6650.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_reference(workload, budget='baseline'):
+    """Bounded CPU sample sized for roughly 10-30 s of work on the box's host cores."""
+    from oracle import cpu_path
+    w = WORKLOADS[workload]
+    cores = cpu_path.host_cores()
+    n_s = max(1, min(cores, w['n_real']))
+    m = 12 * w['nside'] ** 2
+    # ~1 ms of NumPy work per (pixel, realisation) for all five observables
+    target = (12000 if budget == 'baseline' else 20000) * cores
+    frac = min(1.0, target / float(n_s * m))
+    res = cpu_path.time_sample(BOX, [w['G']] * 3, w['nside'], field_descs(w['quantities']),
+                               ensemble_seeds(w['n_real']), LOS_KW, w['n_real'], n_real_sample=n_s,
+                               pixel_fraction=frac, quantities=w['quantities'])
+    return res
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on the host cores, same metric/config, rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    times, last = [], None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        last = cpu_reference(args.workload, budget='reference')
+        wall = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(last['seconds_per_eval'])
+        if wall * (args.warmup + args.steps - i - 1) > 240:      # keep the whole run bounded
+            times = times or [last['seconds_per_eval']]
+            break
+    sec = float(np.mean(times))
+    value = 1.0 / sec
+    line = {
+        'impl': 'reference', 'metric': 'ensemble log-likelihood evals/sec', 'value': value,
+        'unit': 'evals/s', 'n_gpus': args.gpus, 'steps': len(times), 'warmup': args.warmup,
+        'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args.workload, w, 1),
+        'cpu_baseline': {'value': value, 'unit': 'evals/s', 'cores': last['cores'], 'kind': 'port',
+                         'sample': last['sample'], 'stages_s': last['stages']},
+        'e2e': {'value': value, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(name, w, world):
+    return {'workload': '%s: %d^3 grid, Nside %d (m=%d), %d realisations, observables %s @23 GHz, '
+                        'OAS covariance, diagonal measurement covariance'
+                        % (name, w['G'], w['nside'], 12 * w['nside'] ** 2, w['n_real'],
+                           '+'.join(w['quantities'])),
+            'grid': [w['G']] * 3, 'nside': w['nside'], 'ensemble': w['n_real'],
+            'observables': list(w['quantities']), 'los_step_kpc': LOS_KW['dr'],
+            'los_steps': int(np.ceil(LOS_KW['r_max'] / LOS_KW['dr'] - 1e-9)),
+            'parallelism': 'ensemble-sharded x%d' % world, 'l2': 'inputs larger than L2 (B grids)'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from imagine_b200 import _lib, engine
+    from imagine_b200.hotpath import EnsembleEvaluator
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device; there is no CPU fallback '
+                         '(use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    _lib.init(local_rank)
+
+    w = WORKLOADS[args.workload]
+    quantities = w['quantities']
+    N, G, nside = w['n_real'], w['G'], w['nside']
+    m = 12 * nside * nside
+    descs = field_descs(quantities)
+    seeds = ensemble_seeds(N)
+    settings = engine.LosSettings(**LOS_KW)
+    ev = EnsembleEvaluator(BOX, [G] * 3, nside, settings, quantities, n_real=N, rank=rank, world=world)
+
+    # ---- synthetic measurements: one realisation from an independent seed + 1% noise --------
+    mock = EnsembleEvaluator(BOX, [G] * 3, nside, settings, quantities, n_real=1)
+    mock.simulate(descs, np.array([987654321], dtype=np.uint64))
+    gen = torch.Generator(device='cuda').manual_seed(2026)
+    meas_h, var_h = {}, {}
+    for q in quantities:
+        row = mock.local_maps[q][0]
+        sigma = 0.01 * row.abs().mean()
+        meas = row + sigma * torch.randn(m, dtype=torch.float64, device='cuda', generator=gen)
+        meas_h[q] = meas.cpu().pin_memory()
+        var_h[q] = torch.full((m,), float(sigma) ** 2, dtype=torch.float64).pin_memory()
+    del mock
+    meas_d = {q: meas_h[q].cuda() for q in quantities}
+    var_d = {q: var_h[q].cuda() for q in quantities}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps -------------------------------------------------------------------
+    def step(record=None):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record is not None else None
+        if e: e[0].record()
+        f = ev.fields(descs, seeds)
+        if e: e[1].record()
+        ev.los(f)
+        if e: e[2].record()
+        maps = ev.gather()
+        if e: e[3].record()
+        val = ev.loglike(maps, meas_d, var_d)
+        if e:
+            e[4].record()
+            record.append(e)
+        return val
+
+    for _ in range(args.warmup):
+        value_check = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    records = []
+    launches0 = _lib.launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        loglike = step(records)
+    t_end.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    total_ms = t_start.elapsed_time(t_end)
+    stage = np.array([[r[i].elapsed_time(r[i + 1]) for i in range(4)] for r in records]).mean(0)
+
+    # ---- end-to-end steps: host buffers in, host float out -------------------------------------------
+    seeds_h = torch.from_numpy(seeds.astype(np.int64)).pin_memory()
+    h2d = sum(meas_h[q].numel() * 8 + var_h[q].numel() * 8 for q in quantities) + seeds_h.numel() * 8
+
+    def e2e_step():
+        md = {q: meas_h[q].cuda(non_blocking=True) for q in quantities}
+        vd = {q: var_h[q].cuda(non_blocking=True) for q in quantities}
+        sd = seeds_h.cuda(non_blocking=True)                 # seeds travel with the field request
+        ev.simulate(descs, seeds_h.numpy().astype(np.uint64))
+        val = ev.loglike(ev.gather(), md, vd)                # D2H of the scalar happens inside
+        del sd
+        return float(val)
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_val = e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    e2e_wall_ms = (time.perf_counter() - wall0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- max over ranks -------------------------------------------------------------------------------
+    t = torch.tensor([total_ms, e2e_ms, e2e_wall_ms, stage[0], stage[1], stage[2], stage[3]],
+                     dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, e2e_wall_ms = float(t[0]), float(t[1]), float(t[2])
+    stage = [float(v) for v in t[3:7]]
+
+    if rank == 0:
+        n_loc = N // world
+        s_bytes = G ** 3 * 8
+        n_det = 2 if any(q in quantities for q in 'IQU') else 1       # n_e (+ CRE) scalar grids
+        los_bytes = n_loc * 3 * s_bytes + n_det * s_bytes + n_loc * len(quantities) * m * 8
+        field_bytes = n_loc * 3 * s_bytes + n_det * s_bytes
+        peak, peak_kind = measured_peak_gbs()
+        los_gbs = los_bytes / (stage[1] * 1e-3) / 1e9
+        n_steps = settings.n_steps
+        # exact in-box sample count (geometry only)
+        d = ev.dirs
+        r = (torch.arange(n_steps, dtype=torch.float64, device='cuda') + 0.5) * settings.dr
+        obs = torch.tensor(settings.observer, dtype=torch.float64, device='cuda')
+        inbox = 0
+        for s in range(0, m, 8192):
+            pos = obs + r[None, :, None] * d[s:s + 8192, None, :]
+            lo = torch.tensor([b[0] for b in BOX], dtype=torch.float64, device='cuda')
+            hi = torch.tensor([b[1] for b in BOX], dtype=torch.float64, device='cuda')
+            inbox += int(((pos >= lo) & (pos <= hi)).all(-1).sum())
+        line = {
+            'metric': 'ensemble log-likelihood evals/sec', 'value': args.steps / (total_ms * 1e-3),
+            'unit': 'evals/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(args.workload, w, world),
+            'e2e': {'value': args.steps / (max(e2e_ms, e2e_wall_ms) * 1e-3), 'unit': 'evals/s',
+                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 8 * len(quantities) * 14,
+                    'ms_per_step': max(e2e_ms, e2e_wall_ms) / args.steps},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': {'kernel': 'los_kernel', 'bound': 'hbm', 'achieved': los_gbs, 'peak': peak,
+                         'unit': 'GB/s', 'frac': los_gbs / peak, 'traffic': None,
+                         'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)',
+                         'algorithmic_bytes_per_launch': int(los_bytes),
+                         'ms_per_launch': stage[1]},
+            'stages_ms': {'fields': stage[0], 'los': stage[1], 'gather': stage[2], 'likelihood': stage[3]},
+            'field_kernel': {'achieved': field_bytes / (stage[0] * 1e-3) / 1e9, 'unit': 'GB/s',
+                             'frac': field_bytes / (stage[0] * 1e-3) / 1e9 / peak,
+                             'algorithmic_bytes': int(field_bytes)},
+            'los_samples_per_s': {'nominal': n_loc * m * n_steps / (stage[1] * 1e-3),
+                                  'in_box': n_loc * inbox / (stage[1] * 1e-3),
+                                  'in_box_per_realisation': inbox},
+            'loglike': float(loglike),
+        }
+        if not args.no_cpu_baseline:
+            try:
+                res = cpu_reference(args.workload, budget='baseline')
+                line['cpu_baseline'] = {'value': 1.0 / res['seconds_per_eval'], 'unit': 'evals/s',
+                                        'cores': res['cores'], 'kind': 'port', 'sample': res['sample'],
+                                        'stages_s': res['stages']}
+            except Exception as exc:                                      # never lose the GPU line
+                line['cpu_baseline'] = {'value': None, 'unit': 'evals/s', 'cores': 0, 'kind': 'port',
+                                        'sample': 'failed: %r' % (exc,)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
