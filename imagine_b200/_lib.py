@@ -37,7 +37,8 @@ class Grid(C.Structure):
 
 
 class FieldDesc(C.Structure):
-    _fields_ = [('kind', C.c_int32), ('stream', C.c_int32), ('p', C.c_double * 8)]
+    _fields_ = [('kind', C.c_int32), ('stream', C.c_int32), ('seed_row', C.c_int32),
+                ('reserved', C.c_int32), ('p', C.c_double * 8)]
 
 
 class LosCfg(C.Structure):
@@ -55,7 +56,7 @@ _SIGNATURES = {
     'imb_strerror': (C.c_char_p, [C.c_int]),
     'imb_last_cuda_error': (C.c_char_p, []),
     'imb_launch_count': (C.c_int64, []),
-    'imb_field_eval': (C.c_int, [C.POINTER(Grid), C.POINTER(FieldDesc), C.c_int, _P, C.c_int,
+    'imb_field_eval': (C.c_int, [C.POINTER(Grid), C.POINTER(FieldDesc), C.c_int, _P, C.c_int, C.c_int,
                                  _P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     'imb_field_rows': (C.c_int, [C.POINTER(FieldDesc), C.c_int, C.c_int, C.c_int]),
     'imb_test_simulate': (C.c_int, [C.POINTER(Grid), _P, C.c_int, C.c_int, _P, C.c_int, C.c_int,
@@ -161,13 +162,15 @@ def make_grid(box, resolution):
 
 
 def make_field_descs(descs):
-    """descs: iterable of (kind, params, stream) -> ctypes array."""
+    """descs: iterable of (kind, params, stream[, seed_row]) -> ctypes array."""
     descs = list(descs)
     if len(descs) > MAX_FIELDS * 3:
         raise ValueError('too many fields')
     arr = (FieldDesc * max(1, len(descs)))()
-    for i, (kind, params, stream) in enumerate(descs):
+    for i, d in enumerate(descs):
+        kind, params, stream = d[0], d[1], d[2]
         arr[i].kind, arr[i].stream = int(kind), int(stream)
+        arr[i].seed_row = int(d[3]) if len(d) > 3 else 0
         for k, v in enumerate(params):
             arr[i].p[k] = float(v)
     return arr, len(descs)

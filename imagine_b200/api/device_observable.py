@@ -1,0 +1,89 @@
+"""
+`DeviceObservable`: a 'simulated' Observable whose [N, m] block lives in HBM.
+
+`Simulations.append(name=key, data=<Observable instance>)` stores the object as given
+(observables/observable_dict.py:306-307), so the GPU simulator hands the likelihood a
+device-resident ensemble without the reference's per-realisation `np.vstack`
+(observables/observable.py:205).  `.data` is a lazy device->host copy for any host consumer
+(plots, the reference's own likelihoods).
+"""
+import numpy as np
+
+from ._bases import Observable
+
+
+class DeviceObservable(Observable):
+    def __init__(self, tensor, unit=None, coords=None, otype=None):
+        assert tensor.dim() == 2, 'simulated observables are [ensemble, size]'
+        self._dtype = 'simulated'
+        self.otype = otype
+        self.unit = unit
+        self.coords = coords
+        self._rw_flag = False
+        self._tensor = tensor
+        self._host = None
+
+    # device face ----------------------------------------------------------------------------
+    @property
+    def tensor(self):
+        return self._tensor
+
+    def take_rows(self, indices):
+        """Row subset (bootstrap resampling, Simulations.sub_sim) without leaving the device."""
+        import torch
+        idx = torch.as_tensor(np.asarray(indices), device=self._tensor.device)
+        if idx.dtype == torch.bool:
+            idx = idx.nonzero().reshape(-1)
+        return DeviceObservable(self._tensor.index_select(0, idx.long()), self.unit, self.coords, self.otype)
+
+    def take_columns(self, keep):
+        """mask_obs on device (tools/masker.py:25-47)."""
+        import torch
+        from .. import engine
+        idx = torch.as_tensor(np.asarray(keep, dtype=np.int32), device=self._tensor.device)
+        return DeviceObservable(engine.gather_columns(self._tensor, idx), self.unit, self.coords, 'plain')
+
+    # host face (reference contract) -------------------------------------------------------------
+    @property
+    def data(self):
+        if self._host is None:
+            self._host = self._tensor.cpu().numpy()
+        return self._host
+
+    @data.setter
+    def data(self, value):
+        raise AttributeError('DeviceObservable is read-only; build a new one')
+
+    @property
+    def global_data(self):
+        return self.data
+
+    @property
+    def shape(self):
+        return tuple(self._tensor.shape)
+
+    @property
+    def size(self):
+        return int(self._tensor.shape[1])
+
+    @property
+    def ensemble_mean(self):
+        from .. import engine
+        return engine.ensemble_mean(self._tensor).cpu().numpy()
+
+    def append(self, new_data):
+        raise TypeError('DeviceObservable holds the whole ensemble; append is not supported')
+
+    def __getstate__(self):
+        # checkpoints (Pipeline.save, tools/io.py:25-75) must not hold device pointers
+        state = dict(self.__dict__)
+        state['_host'] = self.data
+        state['_tensor'] = None
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        if self._tensor is None and self._host is not None:
+            import torch
+            if torch.cuda.is_available():
+                self._tensor = torch.from_numpy(self._host).cuda()

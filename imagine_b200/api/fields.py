@@ -1,0 +1,150 @@
+"""
+GPU-aware Field plugins: same NAME / PARAMETER_NAMES / TYPE / UNITS as the reference classes,
+plus `device_descriptor()`, which lets `B200Simulator` evaluate the whole ensemble in one fused
+launch instead of calling `get_data` once per realisation.  `compute_field` stays valid for any
+other (host) Simulator: it evaluates ONE realisation on the GPU and returns a host Quantity --
+there is no NumPy implementation behind it.
+
+Reference classes mirrored:
+  ConstantMagneticField            fields/basic_fields.py:16-40
+  ConstantThermalElectrons         fields/basic_fields.py:43-56
+  ExponentialThermalElectrons      fields/basic_fields.py:59-88
+  RandomThermalElectrons           fields/basic_fields.py:91-127
+  CosThermalElectronDensity        fields/test_field.py:19-43
+  NaiveGaussianMagneticField       fields/test_field.py:68-96
+  AnalyticCosmicRayElectrons, ConstantCosmicRayElectrons
+                                   new (reference CRE class is a stub, base_fields.py:104-113);
+                                   parameter names from fields/hamx/cre_analytic.py:19-27
+Stochastic fields draw from Philox4x32-10 keyed on the realisation seed (never on the GPU rank),
+so they match the reference's MT19937 stream in distribution, not bit for bit.
+"""
+import zlib
+
+import numpy as np
+
+from . import units as u
+from ._bases import (MagneticField, ThermalElectronDensityField, CosmicRayElectronDensityField)
+from .. import _lib as L
+
+FLUX_UNIT = (u.GeV * u.m ** 2 * u.s * u.sr) ** (-1)
+
+
+def _stream_id(name):
+    return zlib.crc32(name.encode()) & 0x7fffffff
+
+
+def device_grid(grid):
+    """engine.DeviceGrid for a (mirror or reference) UniformGrid; cached on the object."""
+    from .. import engine
+    dg = getattr(grid, '_imb_device_grid', None)
+    if dg is None:
+        if getattr(grid, 'grid_type', 'cartesian') != 'cartesian':
+            raise ValueError('only cartesian UniformGrids are supported on the GPU path')
+        box = [[float(u.value_in(b, u.kpc)) for b in row] for row in grid.box]
+        dg = engine.DeviceGrid(box, [int(n) for n in grid.resolution])
+        try:
+            grid._imb_device_grid = dg
+        except AttributeError:
+            pass
+    return dg
+
+
+class _DeviceFieldMixin:
+    """Shared machinery: descriptor -> single-realisation evaluation for host consumers."""
+    KIND = None
+    PARAM_UNITS = ()          # canonical unit of each entry of PARAMETER_NAMES
+
+    def _canonical_parameters(self):
+        vals = []
+        for name, unit in zip(self.PARAMETER_NAMES, self.PARAM_UNITS):
+            p = self.parameters[name]
+            if isinstance(p, u.Quantity):
+                try:
+                    p = p.to_value(unit)
+                except Exception:            # e.g. 1/kpc given where rad/kpc is expected
+                    p = p.to_value(unit, u.dimensionless_angles())
+            vals.append(float(p))
+        return vals
+
+    def device_descriptor(self):
+        """(kind, params[<=8], philox_stream) in canonical units (kpc, uG, cm^-3, rad)."""
+        return (self.KIND, self._canonical_parameters(), _stream_id(self.NAME))
+
+    def compute_field(self, seed):
+        from .. import engine
+        dg = device_grid(self.grid)
+        out = engine.field_eval(dg, [self.device_descriptor()], [0 if seed is None else int(seed)],
+                                n_real=1, b_stride=3)
+        (arr,) = out.values()
+        host = arr.cpu().numpy().reshape(self.data_shape)
+        return host * self.UNITS
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state['_deterministic_data'] = None
+        return state
+
+
+class ConstantMagneticField(_DeviceFieldMixin, MagneticField):
+    NAME = 'constant_B'
+    PARAMETER_NAMES = ['Bx', 'By', 'Bz']
+    PARAM_UNITS = (u.microgauss,) * 3
+    KIND = L.FIELD_CONST_B
+
+
+class NaiveGaussianMagneticField(_DeviceFieldMixin, MagneticField):
+    NAME = 'naive_gaussian_magnetic_field'
+    STOCHASTIC_FIELD = True
+    PARAMETER_NAMES = ['a0', 'b0']
+    PARAM_UNITS = (u.microgauss,) * 2
+    KIND = L.FIELD_GAUSS_B
+
+
+class ConstantThermalElectrons(_DeviceFieldMixin, ThermalElectronDensityField):
+    NAME = 'constant_TE'
+    PARAMETER_NAMES = ['ne']
+    PARAM_UNITS = (u.cm ** -3,)
+    KIND = L.FIELD_CONST_NE
+
+
+class ExponentialThermalElectrons(_DeviceFieldMixin, ThermalElectronDensityField):
+    NAME = 'exponential_disc_thermal_electrons'
+    PARAMETER_NAMES = ['central_density', 'scale_radius', 'scale_height']
+    PARAM_UNITS = (u.cm ** -3, u.kpc, u.kpc)
+    KIND = L.FIELD_EXP_NE
+
+
+class RandomThermalElectrons(_DeviceFieldMixin, ThermalElectronDensityField):
+    NAME = 'random_thermal_electrons'
+    STOCHASTIC_FIELD = True
+    PARAMETER_NAMES = ['mean', 'std', 'min_ne']
+    PARAM_UNITS = (u.cm ** -3,) * 3
+    KIND = L.FIELD_RANDOM_NE
+
+
+class CosThermalElectronDensity(_DeviceFieldMixin, ThermalElectronDensityField):
+    NAME = 'cos_therm_electrons'
+    PARAMETER_NAMES = ['n0', 'a', 'alpha', 'b', 'beta', 'c', 'gamma']
+    PARAM_UNITS = (u.cm ** -3, u.rad / u.kpc, u.rad, u.rad / u.kpc, u.rad, u.rad / u.kpc, u.rad)
+    KIND = L.FIELD_COS_NE
+
+
+class AnalyticCosmicRayElectrons(_DeviceFieldMixin, CosmicRayElectronDensityField):
+    """j0 exp(-(R - r_sun)/r0) sech^2(z/z0): CRE flux normalisation at E0 (WMAP-style disc)."""
+    NAME = 'cre_analytic'
+    PARAMETER_NAMES = ['j0', 'r0', 'z0', 'r_sun']
+    PARAM_UNITS = (FLUX_UNIT, u.kpc, u.kpc, u.kpc)
+    KIND = L.FIELD_CRE_ANALYTIC
+
+
+class ConstantCosmicRayElectrons(_DeviceFieldMixin, CosmicRayElectronDensityField):
+    NAME = 'cre_constant'
+    PARAMETER_NAMES = ['j0']
+    PARAM_UNITS = (FLUX_UNIT,)
+    KIND = L.FIELD_CRE_CONST
+
+
+def descriptor_of(field):
+    """Descriptor of a GPU-aware field, or None for a foreign (host-only) Field plugin."""
+    fn = getattr(field, 'device_descriptor', None)
+    return fn() if callable(fn) else None

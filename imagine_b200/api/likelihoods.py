@@ -1,0 +1,185 @@
+"""
+GPU Likelihood drop-ins: same constructors, same `call(simulations_dict) -> float`, same
+assertions as the reference classes
+
+  EnsembleLikelihood           likelihoods/ensemble_likelihood.py:20-107
+  EnsembleLikelihoodDiagonal   likelihoods/ensemble_likelihood.py:110-173
+  SimpleLikelihood             likelihoods/simple_likelihood.py:19-84
+
+Measurements and (co)variances are constant across evaluations, so they are uploaded once
+(after masking, like `Likelihood.measurement_dict`'s setter, likelihood.py:114-148).  Masks
+are applied to the simulated ensemble on the device; the masked key is renamed
+`(name, freq, n_unmasked, tag)` exactly like `Masks.__call__` (observable_dict.py:203-240).
+The simulated block may be a `DeviceObservable` (no copy) or a host `Observable` (uploaded).
+"""
+import numpy as np
+
+from ._bases import Likelihood, Simulations, Masks
+from .device_observable import DeviceObservable
+from .. import engine
+
+
+def _torch():
+    import torch
+    return torch
+
+
+_ESTIMATOR_NAMES = {'oas_mcov': 'oas', 'empirical_mcov': 'empirical', 'diagonal_mcov': 'diagonal',
+                    'oas': 'oas', 'empirical': 'empirical', 'diagonal': 'diagonal'}
+
+
+def _estimator_name(cov_func):
+    """The reference passes a function object (covariance_estimator.py); map it by name."""
+    if cov_func is None:
+        return 'oas'
+    name = cov_func if isinstance(cov_func, str) else getattr(cov_func, '__name__', None)
+    if name not in _ESTIMATOR_NAMES:
+        raise NotImplementedError(
+            'cov_func %r has no CUDA implementation (supported: oas_mcov, empirical_mcov, '
+            'diagonal_mcov); there is no CPU fallback' % (cov_func,))
+    return _ESTIMATOR_NAMES[name]
+
+
+class _DeviceLikelihoodMixin:
+    """Device copies of measurements / covariances and on-device masking of simulations."""
+
+    def _reset_device_state(self):
+        self._dev_meas, self._dev_cov, self._dev_keep = {}, {}, {}
+
+    def _measured(self, key):
+        if key not in self._dev_meas:
+            t = _torch()
+            self._dev_meas[key] = t.from_numpy(
+                np.ascontiguousarray(self._measurement_dict[key].data[0], dtype=np.float64)).cuda()
+        return self._dev_meas[key]
+
+    def _covariance(self, key):
+        """[m] for the 'variance' dtype (never expanded with np.diag), [m,m] otherwise."""
+        if key not in self._dev_cov:
+            t = _torch()
+            obs = self._covariance_dict[key]
+            host = obs.var if obs.dtype == 'variance' else obs.data
+            self._dev_cov[key] = t.from_numpy(np.ascontiguousarray(host, dtype=np.float64)).cuda()
+        return self._dev_cov[key]
+
+    def _variance(self, key):
+        c = self._covariance(key)
+        return c if c.dim() == 1 else c.diagonal().contiguous()
+
+    def _block(self, obs):
+        if isinstance(obs, DeviceObservable):
+            return obs.tensor
+        return _torch().from_numpy(np.ascontiguousarray(obs.data, dtype=np.float64)).cuda()
+
+    def _masked_simulations(self, observable_dict):
+        """Masks.__call__ for the simulated ensemble, on the device."""
+        if self._mask_dict is None:
+            return observable_dict
+        t = _torch()
+        out = Simulations()
+        for name in observable_dict.keys():
+            obs = observable_dict[name]
+            if name not in self._mask_dict.keys():
+                out.append(name=name, data=obs)
+                continue
+            if name not in self._dev_keep:
+                self._dev_keep[name] = t.from_numpy(self._mask_dict.kept_indices(name)).cuda() \
+                    if hasattr(self._mask_dict, 'kept_indices') else \
+                    t.from_numpy(np.flatnonzero(self._mask_dict[name].data[0].astype(bool)).astype(np.int32)).cuda()
+            keep = self._dev_keep[name]
+            block = engine.gather_columns(self._block(obs), keep)
+            new_name = (name[0], name[1], int(keep.numel()), name[3])
+            out.append(name=new_name, data=DeviceObservable(block, obs.unit, obs.coords, 'plain'))
+        return out
+
+    def __call__(self, observable_dict, **kwargs):
+        # same flow as Likelihood.__call__ (likelihood.py:79-92) with the mask step on device
+        observable_dict = self._masked_simulations(observable_dict)
+        value = self.call(observable_dict, **kwargs)
+        if not self.compute_dispersion:
+            return value
+        sample = [self._bootstrapped_likelihood(observable_dict, **kwargs)
+                  for _ in range(self.n_bootstrap)]
+        return value, np.std(sample)
+
+    def _bootstrapped_likelihood(self, simulations, **kwargs):
+        # likelihood.py:94-100: rows resampled with replacement (on the device)
+        size = simulations[next(iter(simulations.keys()))].shape[0]
+        idx = np.random.randint(0, size, size)
+        sub = Simulations()
+        for k in simulations.keys():
+            obs = simulations[k]
+            block = self._block(obs).index_select(0, _torch().from_numpy(idx).cuda())
+            sub.append(name=k, data=DeviceObservable(block, obs.unit, obs.coords, obs.otype))
+        return self.call(sub, **kwargs)
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in ('_dev_meas', '_dev_cov', '_dev_keep'):
+            state[k] = {}
+        return state
+
+
+class B200EnsembleLikelihood(_DeviceLikelihoodMixin, Likelihood):
+    """
+    Gaussian log-likelihood with the covariance of the stochastic fields estimated from the
+    ensemble.  `cov_func` accepts the reference's estimator functions (or their names);
+    `route` = 'auto' | 'gram' | 'dense' selects the O(m N^2) Gram route (diagonal measurement
+    covariance) or the dense DMMA + Cholesky/LU route.
+    """
+
+    def __init__(self, measurement_dict, covariance_dict=None, mask_dict=None, cov_func=None,
+                 use_trace_approximation=False, route='auto', **kwargs):
+        self._reset_device_state()
+        super().__init__(measurement_dict, covariance_dict=covariance_dict, mask_dict=mask_dict, **kwargs)
+        assert self._covariance_dict is not None
+        self.cov_func = cov_func
+        self.estimator = _estimator_name(cov_func)
+        self.use_trace_approximation = use_trace_approximation
+        self.route = route
+
+    def call(self, simulations_dict):
+        assert isinstance(simulations_dict, Simulations)
+        assert set(simulations_dict.keys()).issubset(self._measurement_dict.keys())
+        assert set(simulations_dict.keys()).issubset(self._covariance_dict.keys())
+        total = 0.
+        for name in simulations_dict:
+            total += engine.loglike_ensemble(
+                self._block(simulations_dict[name]), self._measured(name), self._covariance(name),
+                estimator=self.estimator, route=self.route,
+                use_trace_approximation=self.use_trace_approximation)
+        return total
+
+
+class B200EnsembleLikelihoodDiagonal(_DeviceLikelihoodMixin, Likelihood):
+    def __init__(self, measurement_dict, covariance_dict=None, mask_dict=None, **kwargs):
+        self._reset_device_state()
+        super().__init__(measurement_dict, covariance_dict=covariance_dict, mask_dict=mask_dict, **kwargs)
+        assert self._covariance_dict is not None
+
+    def call(self, simulations_dict):
+        assert isinstance(simulations_dict, Simulations)
+        assert set(simulations_dict.keys()).issubset(self._measurement_dict.keys())
+        assert set(simulations_dict.keys()).issubset(self._covariance_dict.keys())
+        total = 0.
+        for name in simulations_dict.keys():
+            total += engine.loglike_ensemble_diagonal(self._block(simulations_dict[name]),
+                                                      self._measured(name), self._variance(name))
+        return total
+
+
+class B200SimpleLikelihood(_DeviceLikelihoodMixin, Likelihood):
+    def __init__(self, measurement_dict, covariance_dict=None, mask_dict=None, **kwargs):
+        self._reset_device_state()
+        super().__init__(measurement_dict, covariance_dict=covariance_dict, mask_dict=mask_dict, **kwargs)
+
+    def call(self, simulations_dict):
+        assert isinstance(simulations_dict, Simulations)
+        assert set(simulations_dict.keys()).issubset(self._measurement_dict.keys())
+        cov_keys = self._covariance_dict.keys() if self._covariance_dict is not None else ()
+        total = 0
+        for name in self._measurement_dict:          # KeyError if a measurement was not simulated
+            sims = self._block(simulations_dict[name])
+            cov = self._covariance(name) if name in cov_keys else None
+            total += engine.loglike_simple(sims, self._measured(name), cov)
+        return total

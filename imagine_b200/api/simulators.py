@@ -1,0 +1,328 @@
+"""
+GPU Simulator drop-ins.
+
+`B200Simulator` takes the place of `imagine.simulators.Hammurabi`
+(simulators/hammurabi.py:29-346: observables 'fd', 'dm', 'sync'; units K / rad m^-2 /
+pc cm^-3; RING-ordered HEALPix maps of length 12 Nside^2) without the XML / temp-file /
+subprocess round trip: fields are evaluated on the device grid and integrated along the
+lines of sight by the CUDA kernels.  `B200TestSimulator` mirrors
+`imagine.simulators.TestSimulator` (simulators/test_simulator.py:19-69).
+
+Both override `Simulator.__call__` -- still the public entry `Pipeline._get_observables`
+uses (pipelines/pipeline.py:850) -- to evaluate the WHOLE ensemble in one batched pass instead
+of the reference's N x K Python loop (simulator.py:411-421), and return a `Simulations`
+dictionary of device-resident `DeviceObservable`s.  `simulate(key, coords_dict,
+realization_id, output_units)` stays valid for the base-class loop and for foreign callers:
+it integrates the host fields found in `self.fields` for one realisation.
+
+Field plugins that expose `device_descriptor()` (api/fields.py) are fused into one launch;
+any other `Field` subclass still works -- its `get_data` arrays are uploaded and summed on
+the device.
+"""
+import numpy as np
+
+from . import units as u
+from ._bases import Simulator, Simulations
+from .device_observable import DeviceObservable
+from .fields import descriptor_of, device_grid
+from .. import engine
+from ..hotpath import shard_bounds
+
+FIELD_UNITS = {'magnetic_field': u.microgauss, 'thermal_electron_density': u.cm ** -3}
+_NAMES = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _host_values(q, unit):
+    """Plain float64 array of a field returned by Field.get_data, in canonical units."""
+    if isinstance(q, u.Quantity):
+        return np.asarray(q.to_value(unit) if unit is not None else q.value, dtype=np.float64)
+    return np.asarray(q, dtype=np.float64)
+
+
+def _accepted_fields(sim, field_list):
+    """Fields `sim` consumes after the grid checks of Simulator.prepare_fields (simulator.py:128-147)."""
+    wanted = (*sim.required_field_types, *sim.optional_field_types)
+    sim.grid, sim.grids = None, None
+    used = []
+    for f in field_list:
+        if f.type not in wanted:
+            continue
+        if f.grid is not None and sim.allowed_grid_types is not None:
+            assert f.grid.grid_type in sim.allowed_grid_types, 'Grid type not allowed'
+        if sim.grid is None:
+            sim.grid = f.grid
+        assert sim.grid is f.grid, 'Multiple grids when a common grid is required'
+        used.append(f)
+    assert set(sim.required_field_types) <= {f.type for f in used}, 'Missing required field'
+    return used
+
+
+class _DeviceFieldEvaluator:
+    """Evaluates a list of Field plugins for a block of realisations into device buffers."""
+
+    def __init__(self, b_stride):
+        self.b_stride = b_stride
+
+    def evaluate(self, fields, grid, lo, hi):
+        torch = _torch()
+        n_local = hi - lo
+        dg = device_grid(grid)
+        descs, seed_rows, foreign = [], [], []
+        for f in fields:
+            d = descriptor_of(f)
+            if d is None:
+                foreign.append(f)
+                continue
+            row = 0
+            if f.stochastic_field:
+                seed_rows.append(np.asarray(f.ensemble_seeds, dtype=np.uint64)[lo:hi])
+                row = len(seed_rows) - 1
+            descs.append((d[0], d[1], d[2], row))
+        seeds = np.stack(seed_rows) if seed_rows else np.zeros((1, n_local), dtype=np.uint64)
+        out = engine.field_eval(dg, descs, seeds, n_real=n_local, b_stride=self.b_stride) if descs else {}
+        # foreign plugins: host get_data -> upload -> device sum (simulator.py:166-178 semantics)
+        for f in foreign:
+            unit = FIELD_UNITS.get(f.type, f.units)
+            rows = n_local if f.stochastic_field else 1
+            host = np.stack([_host_values(f.get_data(lo + i), unit) for i in range(rows)])
+            if f.type == 'magnetic_field':
+                dev = torch.zeros((rows, dg.ncell, self.b_stride), dtype=torch.float64, device='cuda')
+                dev[:, :, :3] = torch.from_numpy(host.reshape(rows, dg.ncell, 3)).cuda()
+            else:
+                dev = torch.from_numpy(host.reshape(rows, dg.ncell)).cuda()
+            cur = out.get(f.type)
+            out[f.type] = dev if cur is None else cur + dev       # broadcasts 1 <-> n_local rows
+        return dg, out
+
+
+class B200Simulator(Simulator):
+    """
+    Faraday depth, dispersion measure and synchrotron Stokes maps on the GPU.
+
+    Parameters
+    ----------
+    measurements : Measurements
+        keys ('fd', None, Nside, None), ('dm', None, Nside, None),
+        ('sync', freq_GHz, Nside, 'I'|'Q'|'U'|'PI'|'PA')   (observable_dict.py:11-25)
+    observer : 3 floats [kpc]           (hammurabi XML grid/observer, test_ham.xml:26-30)
+    radial_step, radial_max : [kpc]     (oc_r_res, oc_r_max, test_ham.xml:122-131)
+    cre_alpha, cre_beta, cre_theta, cre_E0 : CRE spectrum p = alpha - beta R - theta z at E0 [GeV]
+                                        (fields/hamx/cre_analytic.py:19-27)
+    rank, world, group : ensemble sharding over torch.distributed ranks (pipeline.py:737-744)
+    """
+    SIMULATED_QUANTITIES = ['fd', 'dm', 'sync']
+    REQUIRED_FIELD_TYPES = ['magnetic_field']
+    OPTIONAL_FIELD_TYPES = ['thermal_electron_density', 'cosmic_ray_electron_density']
+    ALLOWED_GRID_TYPES = ['cartesian']
+
+    def __init__(self, measurements, observer=(-8.3, 0.0, 0.006), radial_step=0.1, radial_max=30.0,
+                 cre_alpha=3.0, cre_beta=0.0, cre_theta=0.0, cre_E0=20.6, b_stride=4,
+                 rank=0, world=1, group=None):
+        super().__init__(measurements)
+        self.los_kwargs = dict(observer=tuple(float(u.value_in(v, u.kpc)) for v in observer),
+                               dr=float(u.value_in(radial_step, u.kpc)),
+                               r_max=float(u.value_in(radial_max, u.kpc)),
+                               alpha=float(cre_alpha), beta=float(cre_beta), theta=float(cre_theta),
+                               e0_gev=float(cre_E0))
+        self.b_stride = int(b_stride)
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self._dirs = {}
+        self._row_cache = (None, {})
+        for key in self.observables:
+            name, freq, nside, tag = key
+            if nside == 'tab':
+                raise NotImplementedError('Tabular datasets not yet supported!')   # hammurabi.py:340-341
+            if name == 'sync':
+                if tag not in ('I', 'Q', 'U', 'PI', 'PA'):
+                    raise ValueError('unrecognised synchrotron tag %r' % (tag,))
+                if freq is None:
+                    raise ValueError('synchrotron observables need a frequency')
+
+    # -- unit handling (hammurabi.py:214-227) ---------------------------------------------------
+    @staticmethod
+    def _units(key):
+        if key[0] == 'sync':
+            if key[3] in ('I', 'Q', 'U', 'PI'):
+                return u.K
+            if key[3] == 'PA':
+                return u.rad
+            raise ValueError
+        if key[0] == 'fd':
+            return u.rad / u.m / u.m
+        if key[0] == 'dm':
+            return u.pc / u.cm ** 3
+        raise ValueError
+
+    def _scale(self, key):
+        out_unit = self.output_units.get(key)
+        return 1.0 if out_unit is None else u.unit_scale(self._units(key), out_unit)
+
+    def _dirs_for(self, nside):
+        if nside not in self._dirs:
+            self._dirs[nside] = engine.healpix_ring_dirs(int(nside))
+        return self._dirs[nside]
+
+    # -- the integrator for a block of realisations --------------------------------------------------
+    def _integrate(self, dg, fields, n_real):
+        """{key: tensor [n_real, m]} for every registered observable."""
+        torch = _torch()
+        B = fields['magnetic_field']
+        ne = fields.get('thermal_electron_density')
+        cre = fields.get('cosmic_ray_electron_density')
+        # group by (nside, frequency): one launch each; fd/dm ride with the first group of their nside
+        groups = {}
+        for key in self.observables:
+            name, freq, nside, tag = key
+            groups.setdefault(int(nside), {}).setdefault(None if name != 'sync' else float(freq), []).append(key)
+        result = {}
+        for nside, by_freq in groups.items():
+            dirs = self._dirs_for(nside)
+            freqs = [f for f in by_freq if f is not None]
+            plain = by_freq.get(None, [])
+            launches = [(f, by_freq[f] + (plain if i == 0 else [])) for i, f in enumerate(freqs)]
+            if not freqs:
+                launches = [(None, plain)]
+            for freq, keys in launches:
+                want = set()
+                for k in keys:
+                    if k[0] in ('fd', 'dm'):
+                        want.add(k[0])
+                    elif k[3] in ('I', 'Q', 'U'):
+                        want.add(k[3])
+                    else:
+                        want.update(('Q', 'U'))
+                if want & {'fd', 'dm'} and ne is None:
+                    raise AssertionError("'fd'/'dm' need a thermal_electron_density field")
+                if want & {'I', 'Q', 'U'} and cre is None:
+                    raise AssertionError("'sync' needs a cosmic_ray_electron_density field")
+                kw = dict(self.los_kwargs)
+                if freq is not None:
+                    kw['nu_ghz'] = freq
+                maps = engine.los_integrate(dg, engine.LosSettings(**kw), dirs, B, ne,
+                                            cre if want & {'I', 'Q', 'U'} else None,
+                                            n_real=n_real, want=tuple(want))
+                derived = None
+                for k in keys:
+                    if k[0] in ('fd', 'dm'):
+                        t = maps[k[0]]
+                    elif k[3] in ('I', 'Q', 'U'):
+                        t = maps[k[3]]
+                    else:
+                        if derived is None:
+                            derived = engine.pol_derive(maps['Q'], maps['U'])
+                        t = derived[0] if k[3] == 'PI' else derived[1]
+                    s = self._scale(k)
+                    result[k] = t if s == 1.0 else t * s
+        return result
+
+    # -- batched public entry -----------------------------------------------------------------------
+    def __call__(self, field_list):
+        self.register_ensemble_size(field_list)
+        fields = _accepted_fields(self, field_list)
+        N = self._ensemble_size
+        lo, hi = shard_bounds(N, self.rank, self.world)
+        dg, dev_fields = _DeviceFieldEvaluator(self.b_stride).evaluate(fields, self.grid, lo, hi)
+        maps = self._integrate(dg, dev_fields, hi - lo)
+        sims = Simulations()
+        for key in self.observables:
+            block = maps[key]
+            if self.world > 1:
+                import torch.distributed as dist
+                full = _torch().empty((N, block.shape[1]), dtype=block.dtype, device=block.device)
+                dist.all_gather_into_tensor(full, block.contiguous(), group=self.group)
+                block = full
+            unit = self.output_units.get(key) or self._units(key)
+            sims.append(name=key, data=DeviceObservable(block, unit, self.output_coords[key],
+                                                        self.output_type[key]),
+                        coords=self.output_coords[key], otype=self.output_type[key])
+        return sims
+
+    # -- per-realisation contract (simulator.py:370-393) -----------------------------------------------
+    def simulate(self, key, coords_dict, realization_id, output_units):
+        torch = _torch()
+        cached_id, rows = self._row_cache
+        if cached_id != realization_id or key not in rows:
+            assert self.fields is not None and 'magnetic_field' in self.fields, 'prepare_fields first'
+            dg = device_grid(self.grid)
+            dev = {}
+            for name in _NAMES:
+                if name not in self.fields:
+                    continue
+                host = _host_values(self.fields[name], FIELD_UNITS.get(name))
+                if name == 'magnetic_field':
+                    t = torch.zeros((1, dg.ncell, self.b_stride), dtype=torch.float64, device='cuda')
+                    t[:, :, :3] = torch.from_numpy(host.reshape(1, dg.ncell, 3)).cuda()
+                else:
+                    t = torch.from_numpy(host.reshape(1, dg.ncell)).cuda()
+                dev[name] = t
+            rows = {k: v[0].cpu().numpy() for k, v in self._integrate(dg, dev, 1).items()}
+            self._row_cache = (realization_id, rows)
+        unit = self.output_units.get(key) or self._units(key)
+        return rows[key] * unit
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state['_dirs'] = {}
+        state['_row_cache'] = (None, {})
+        state['group'] = None
+        return state
+
+
+class B200TestSimulator(Simulator):
+    """t(x,y,z) = B_axis * n_e at the nearest grid vertex of each tabulated point (no integration)."""
+    SIMULATED_QUANTITIES = ['test']
+    REQUIRED_FIELD_TYPES = ['magnetic_field', 'thermal_electron_density']
+    ALLOWED_GRID_TYPES = ['cartesian']
+    __test__ = False
+
+    def __init__(self, measurements, LoS_axis='y'):
+        super().__init__(measurements)
+        if LoS_axis == 'y':
+            self.B_axis = 1
+        elif LoS_axis == 'z':
+            self.B_axis = 2
+        else:
+            raise ValueError
+
+    def _points(self, coords_dict):
+        torch = _torch()
+        pts = np.array([np.atleast_1d(u.value_in(coords_dict[c], u.kpc)) for c in ('x', 'y', 'z')],
+                       dtype=np.float64).T
+        return torch.from_numpy(np.ascontiguousarray(pts)).cuda()
+
+    def _scale(self, key):
+        out_unit = self.output_units.get(key)
+        native = u.microgauss * u.cm ** -3
+        return 1.0 if out_unit is None else u.unit_scale(native, out_unit)
+
+    def __call__(self, field_list):
+        self.register_ensemble_size(field_list)
+        fields = _accepted_fields(self, field_list)
+        N = self._ensemble_size
+        dg, dev = _DeviceFieldEvaluator(3).evaluate(fields, self.grid, 0, N)
+        sims = Simulations()
+        for key in self.observables:
+            block = engine.test_simulate(dg, dev['magnetic_field'], dev['thermal_electron_density'], N,
+                                         self._points(self.output_coords[key]), b_axis=self.B_axis,
+                                         scale=self._scale(key))
+            unit = self.output_units.get(key) or (u.microgauss * u.cm ** -3)
+            sims.append(name=key, data=DeviceObservable(block, unit, self.output_coords[key],
+                                                        self.output_type[key]),
+                        coords=self.output_coords[key], otype=self.output_type[key])
+        return sims
+
+    def simulate(self, key, coords_dict, realization_id, output_units):
+        torch = _torch()
+        dg = device_grid(self.grid)
+        B = _host_values(self.fields['magnetic_field'], u.microgauss).reshape(1, dg.ncell, 3)
+        ne = _host_values(self.fields['thermal_electron_density'], u.cm ** -3).reshape(1, dg.ncell)
+        native = u.microgauss * u.cm ** -3
+        scale = 1.0 if output_units is None else u.unit_scale(native, output_units)
+        row = engine.test_simulate(dg, torch.from_numpy(B).cuda(), torch.from_numpy(ne).cuda(), 1,
+                                   self._points(coords_dict), b_axis=self.B_axis, scale=scale)
+        return row[0].cpu().numpy() * (output_units if output_units is not None else native)

@@ -15,8 +15,10 @@ struct FieldArgs {
   int rows;                 // 1 or n_real
   int kind[IMB_MAX_FIELDS];
   unsigned int stream[IMB_MAX_FIELDS];
+  int seed_row[IMB_MAX_FIELDS];
   double p[IMB_MAX_FIELDS][8];
-  const unsigned long long* seeds;  // device [n_real]
+  int n_real;                       // seeds row length
+  const unsigned long long* seeds;  // device [n_seed_rows, n_real]
 };
 
 __device__ __forceinline__ void cell_xyz(const DevGrid& g, long long c, double& x, double& y,
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(256) field_b_kernel(const __grid_constant__ Fi
 #pragma unroll
         for (int k = 0; k < 6; ++k) t[k] = a.p[f][k % 3];
       } else {  // IMB_FIELD_GAUSS_B: flat normal index n = 3*cell + comp, block n >> 1
-        const unsigned long long seed = a.seeds[r];
+        const unsigned long long seed = a.seeds[(size_t)a.seed_row[f] * a.n_real + r];
         const double mu = a.p[f][0], sigma = a.p[f][1];
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
@@ -135,7 +137,8 @@ __global__ void __launch_bounds__(256) field_scalar_kernel(const __grid_constant
       double t0, t1;
       if (a.kind[f] == IMB_FIELD_RANDOM_NE) {
         double n0, n1;
-        philox_normal_pair(a.seeds[r], a.stream[f], (unsigned long long)q, n0, n1);
+        philox_normal_pair(a.seeds[(size_t)a.seed_row[f] * a.n_real + r], a.stream[f],
+                           (unsigned long long)q, n0, n1);
         t0 = __dadd_rn(__dmul_rn(n0, a.p[f][1]), a.p[f][0]);
         t1 = __dadd_rn(__dmul_rn(n1, a.p[f][1]), a.p[f][0]);
         const double mn = a.p[f][2];
@@ -311,8 +314,9 @@ int imb_field_rows(const imb_field_desc* fields, int nfields, int type, int n_re
 }
 
 int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfields,
-                   const uint64_t* seeds, int n_real, double* out_B, int rows_B, int b_stride,
-                   double* out_ne, int rows_ne, double* out_cre, int rows_cre, void* stream_) {
+                   const uint64_t* seeds, int n_seed_rows, int n_real, double* out_B, int rows_B,
+                   int b_stride, double* out_ne, int rows_ne, double* out_cre, int rows_cre,
+                   void* stream_) {
   IMB_TRY(check_init());
   cudaStream_t stream = (cudaStream_t)stream_;
   DevGrid g;
@@ -323,13 +327,19 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
     if (field_type(fields[f].kind) < 0) return IMB_EINVAL;
 
   // seeds -> device scratch (pageable H2D is staged before the call returns)
-  IMB_TRY(ensure_workspace(sizeof(unsigned long long) * (size_t)n_real + 256));
+  if (n_seed_rows < 0) return IMB_EINVAL;
+  const size_t n_seeds = (size_t)(n_seed_rows > 0 ? n_seed_rows : 1) * (size_t)n_real;
+  IMB_TRY(ensure_workspace(sizeof(unsigned long long) * n_seeds + 256));
   unsigned long long* d_seeds = static_cast<unsigned long long*>(state().ws);
   bool any_stochastic = false;
-  for (int f = 0; f < nfields; ++f) any_stochastic |= is_stochastic(fields[f].kind);
+  for (int f = 0; f < nfields; ++f) {
+    if (!is_stochastic(fields[f].kind)) continue;
+    any_stochastic = true;
+    if (fields[f].seed_row < 0 || fields[f].seed_row >= n_seed_rows) return IMB_EINVAL;
+  }
   if (any_stochastic) {
     if (!seeds) return IMB_EINVAL;
-    IMB_CUDA(cudaMemcpyAsync(d_seeds, seeds, sizeof(unsigned long long) * (size_t)n_real,
+    IMB_CUDA(cudaMemcpyAsync(d_seeds, seeds, sizeof(unsigned long long) * n_seeds,
                              cudaMemcpyHostToDevice, stream));
   }
 
@@ -344,12 +354,14 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
     a.g = g;
     a.rows = need;
     a.seeds = d_seeds;
+    a.n_real = n_real;
     a.nfields = 0;
     for (int f = 0; f < nfields; ++f) {
       if (field_type(fields[f].kind) != type) continue;
       if (a.nfields == IMB_MAX_FIELDS) return IMB_EUNSUPPORTED;
       a.kind[a.nfields] = fields[f].kind;
       a.stream[a.nfields] = (unsigned int)fields[f].stream;
+      a.seed_row[a.nfields] = fields[f].seed_row;
       for (int k = 0; k < 8; ++k) a.p[a.nfields][k] = fields[f].p[k];
       a.nfields++;
     }

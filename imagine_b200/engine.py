@@ -77,15 +77,16 @@ def field_eval(grid, descs, seeds, n_real=None, b_stride=4, out=None):
     Evaluate and sum all fields (imb_field_eval).  Returns dict with any of
     'magnetic_field' [rows, ncell, b_stride], 'thermal_electron_density' [rows, ncell],
     'cosmic_ray_electron_density' [rows, ncell]; rows is n_real when a stochastic field of the
-    type is present and 1 otherwise.
+    type is present and 1 otherwise.  `descs` entries are (kind, params, philox_stream[, seed_row]);
+    `seeds` is [n_real] or [n_seed_rows, n_real].
     """
     torch = _torch()
     dev = L.init()
-    seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64).reshape(-1))
+    seeds = np.ascontiguousarray(np.atleast_2d(np.asarray(seeds, dtype=np.uint64)))
     if n_real is None:
-        n_real = int(seeds.size)
-    if seeds.size != n_real:
-        raise ValueError('need one seed per realisation')
+        n_real = int(seeds.shape[1])
+    if seeds.ndim != 2 or seeds.shape[1] != n_real:
+        raise ValueError('need one seed per realisation (rows = seed lists)')
     arr, n = L.make_field_descs(descs)
     rows = field_rows(descs, n_real)
     names = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
@@ -103,7 +104,7 @@ def field_eval(grid, descs, seeds, n_real=None, b_stride=4, out=None):
         bufs[name] = buf
     B, ne, cre = (bufs.get(k) for k in names)
     L.check(L.load().imb_field_eval(
-        C.byref(grid.c), arr, n, seeds.ctypes.data_as(C.c_void_p), n_real,
+        C.byref(grid.c), arr, n, seeds.ctypes.data_as(C.c_void_p), int(seeds.shape[0]), n_real,
         L.ptr(B), rows[0], b_stride, L.ptr(ne), rows[1], L.ptr(cre), rows[2], L.stream_ptr()))
     return bufs
 

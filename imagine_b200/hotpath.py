@@ -55,8 +55,8 @@ class EnsembleEvaluator:
     # -- stage 1 + 2 -----------------------------------------------------------------------
     def fields(self, descs, seeds):
         """Evaluate this rank's realisations; buffers are reused across evaluations."""
-        seeds = np.asarray(seeds, dtype=np.uint64).reshape(-1)
-        if seeds.size != self.n_real:
+        seeds = np.atleast_2d(np.asarray(seeds, dtype=np.uint64))
+        if seeds.shape[1] != self.n_real:
             raise ValueError('need one seed per (global) realisation')
         rows = engine.field_rows(descs, self.n_local)
         names = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
@@ -70,7 +70,7 @@ class EnsembleEvaluator:
                 buf = self.torch.empty(shape, dtype=self.torch.float64, device=self.dirs.device)
                 self._field_bufs[name] = buf
             out[name] = buf
-        return engine.field_eval(self.grid, descs, seeds[self.lo:self.hi], n_real=self.n_local,
+        return engine.field_eval(self.grid, descs, seeds[:, self.lo:self.hi], n_real=self.n_local,
                                  b_stride=self.b_stride, out=out)
 
     def los(self, fields):

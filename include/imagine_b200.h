@@ -65,6 +65,8 @@ enum {
 typedef struct {
   int32_t kind;     /* IMB_FIELD_*                                                        */
   int32_t stream;   /* Philox stream id: decorrelates stochastic fields sharing a seed    */
+  int32_t seed_row; /* row of the `seeds` table this field draws from (each FieldFactory  */
+  int32_t reserved; /* owns its own seed list, pipelines/pipeline.py:805-813)             */
   double p[8];      /* parameters in canonical units                                      */
 } imb_field_desc;
 
@@ -105,7 +107,8 @@ int64_t imb_launch_count(void);
  * Replaces, for all realisations at once: Field.get_data (fields/field.py:135-173),
  * the compute_field bodies cited above and the same-type sum in
  * Simulator.prepare_fields (simulators/simulator.py:166-178).
- *   seeds      HOST [n_real] ensemble seeds (Field.ensemble_seeds), global order
+ *   seeds      HOST [n_seed_rows, n_real] ensemble seeds (Field.ensemble_seeds), one row per
+ *              seed list; fields[f].seed_row selects the row of a stochastic field
  *   out_B      [rows_B, ncell, b_stride]  b_stride = 3 (reference layout, component
  *              innermost) or 4 (padded, 4th component = 0); rows_* is n_real if a
  *              stochastic field of that type is present, else 1 (IMB_EINVAL otherwise)
@@ -113,7 +116,7 @@ int64_t imb_launch_count(void);
  * A NULL output skips that field type.  Asynchronous.
  */
 int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfields,
-                   const uint64_t* seeds, int n_real,
+                   const uint64_t* seeds, int n_seed_rows, int n_real,
                    double* out_B, int rows_B, int b_stride,
                    double* out_ne, int rows_ne,
                    double* out_cre, int rows_cre, void* stream);

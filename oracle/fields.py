@@ -208,21 +208,25 @@ def random_ne_philox(grid, mean, std, min_ne, seed, stream):
 # ------------------------------------------------------------------ descriptor evaluator
 def evaluate_fields(grid, descs, seeds, rng='philox'):
     """
-    Mirror of the C-ABI ``imb_field_eval``.  ``descs`` = list of (kind, params, stream);
-    ``seeds`` = per-realisation seeds (global realisation order).  Same-type fields are
+    Mirror of the C-ABI ``imb_field_eval``.  ``descs`` = list of (kind, params, stream[, seed_row]);
+    ``seeds`` = per-realisation seeds [n_real] or a table [n_seed_rows, n_real] (one row per
+    FieldFactory seed list; ``seed_row`` picks the row).  Same-type fields are
     summed left to right (simulator.py:175-178).  Returns {field_type: array} where the
     array has a leading realisation axis of length len(seeds) if any contributing field
     is stochastic, else length 1.
     """
-    nreal = len(seeds)
+    seed_table = np.atleast_2d(np.asarray(seeds, dtype=np.uint64))
+    nreal = seed_table.shape[1]
+    descs = [tuple(d) + (0,) if len(d) == 3 else tuple(d) for d in descs]
     out = {}
-    for ftype in dict.fromkeys(TYPE_OF_KIND[k] for k, _, _ in descs):
+    for ftype in dict.fromkeys(TYPE_OF_KIND[d[0]] for d in descs):
         mine = [d for d in descs if TYPE_OF_KIND[d[0]] == ftype]
-        stochastic = any(k in STOCHASTIC_KINDS for k, _, _ in mine)
+        stochastic = any(d[0] in STOCHASTIC_KINDS for d in mine)
         reals = []
         for r in range(nreal if stochastic else 1):
             total = None
-            for kind, p, stream in mine:
+            for kind, p, stream, row in mine:
+                seeds = seed_table[row]
                 if kind == CONST_B:
                     f = constant_B(grid, *p[:3])
                 elif kind == GAUSS_B:

@@ -52,5 +52,5 @@ def test_compute_entry_points_refuse_without_init(lib):
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_lib.Grid) == 64
-    assert C.sizeof(_lib.FieldDesc) == 72
+    assert C.sizeof(_lib.FieldDesc) == 80
     assert C.sizeof(_lib.LosCfg) == 88

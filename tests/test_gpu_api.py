@@ -1,0 +1,267 @@
+"""
+GPU: the reference-facing drop-ins (Field / Simulator / Likelihood plugins).  The likelihood
+tests are the reference's own imagine/tests/test_likelihood.py with the GPU classes swapped in;
+the pipeline test follows imagine/tests/test_templates.py:146-219 (golden -55.581767201053125).
+"""
+import pickle
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import fields as OF           # noqa: E402
+from oracle import healpix as OH          # noqa: E402
+from oracle import likelihood as OK       # noqa: E402
+from oracle import los as OL              # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def api():
+    import torch
+    assert torch.cuda.is_available()
+    import imagine_b200.api as api
+    from imagine_b200 import _lib
+    _lib.init(0)
+    return api
+
+
+# ------------------------------------------------------------ reference test_likelihood.py, GPU classes
+def test_simple_without_cov(api):
+    simdict, meadict = api.Simulations(), api.Measurements()
+    arr_a, arr_b = np.random.rand(1, 48), np.random.rand(3, 48)
+    meadict.append(name=('test', None, 2, None), data=api.Observable(arr_a, 'measured'), otype='HEALPix')
+    simdict.append(name=('test', None, 2, None), data=api.Observable(arr_b, 'simulated'), otype='HEALPix')
+    result = api.B200SimpleLikelihood(meadict)(simdict)
+    diff = np.mean(arr_b, axis=0) - arr_a
+    assert np.allclose(result, -0.5 * float(np.vdot(diff, diff)))
+
+
+def test_simple_with_cov(api):
+    simdict, meadict, covdict = api.Simulations(), api.Measurements(), api.Covariances()
+    arr_a, arr_b, arr_c = np.random.rand(1, 4), np.random.rand(5, 4), np.random.rand(4, 4)
+    key = ('test', None, 4, None)
+    meadict.append(name=key, data=api.Observable(arr_a, 'measured'), otype='plain')
+    simdict.append(name=key, data=api.Observable(arr_b, 'simulated'), otype='plain')
+    covdict.append(name=key, cov_data=api.Observable(arr_c, 'covariance'))
+    result = api.B200SimpleLikelihood(meadict, covdict)(simdict)
+    diff = np.mean(arr_b, axis=0) - arr_a
+    sign, logdet = np.linalg.slogdet(arr_c * 2. * np.pi)
+    baseline = -0.5 * (np.vdot(diff, np.linalg.solve(arr_c, diff.T)) + sign * logdet)
+    assert np.allclose(result, baseline)
+
+
+@pytest.mark.parametrize('trace', [False, True])
+def test_ensemble_equals_simple_for_identical_realisations(api, trace):
+    for _ in range(5):
+        simdict, meadict, covdict = api.Simulations(), api.Measurements(), api.Covariances()
+        key = ('test', None, 4, None)
+        meadict.append(name=key, data=api.Observable(np.random.rand(1, 4), 'measured'), otype='plain')
+        arr_c = np.diag(np.random.rand(4)) if trace else np.random.rand(4, 4)
+        covdict.append(name=key, cov_data=api.Observable(arr_c, 'covariance'))
+        arr_ens = np.repeat(np.random.rand(1, 4), 2, axis=0)
+        simdict.append(name=key, data=api.Observable(arr_ens, 'simulated'), otype='plain')
+        result_simple = api.B200SimpleLikelihood(meadict, covdict)(simdict)
+        result_ensemble = api.B200EnsembleLikelihood(meadict, covdict, use_trace_approximation=trace)(simdict)
+        assert result_ensemble == result_simple
+
+
+def test_diag(api):
+    simdict, meadict, covdict = api.Simulations(), api.Measurements(), api.Covariances()
+    key = ('test', None, 40, None)
+    meadict.append(name=key, data=api.Observable(np.random.rand(1, 40), 'measured'), otype='plain')
+    covdict.append(name=key, cov_data=api.Observable(np.diag(np.random.rand(40)), 'covariance'))
+    simdict.append(name=key, data=api.Observable(np.random.rand(10, 40), 'simulated'), otype='plain')
+
+    def diagonal_mcov(data):                  # the reference passes the function object
+        raise AssertionError('mapped by name, never called on the host')
+    result_ens = api.B200EnsembleLikelihood(meadict, covdict, cov_func=diagonal_mcov)(simdict)
+    result_diag = api.B200EnsembleLikelihoodDiagonal(meadict, covdict)(simdict)
+    assert np.allclose(result_diag, result_ens)
+    with pytest.raises(NotImplementedError):
+        api.B200EnsembleLikelihood(meadict, covdict, cov_func=lambda d: (d.mean(0), np.eye(40)))
+
+
+def test_goldens_through_the_plugin_api(api, golden_likelihood):
+    cls = {'ensemble': api.B200EnsembleLikelihood, 'ensemble_diagonal': api.B200EnsembleLikelihoodDiagonal,
+           'simple': api.B200SimpleLikelihood}
+    for name, c in golden_likelihood.items():
+        m = c['sims'].shape[1]
+        key = ('test', None, m, None)
+        M, C, S = api.Measurements(), api.Covariances(), api.Simulations()
+        M.append(name=key, data=c['meas'].reshape(1, -1), otype='plain')
+        S.append(name=key, data=c['sims'], otype='plain')
+        if c['cov'] is not None:
+            C.append(name=key, cov_data=c['cov'], otype='plain')
+        masks = None
+        if c['mask'] is not None:
+            masks = api.Masks()
+            masks.append(name=key, data=c['mask'].reshape(1, -1), otype='plain')
+        kw = {}
+        if c['kind'] == 'ensemble':
+            kw = dict(cov_func=str(c['estimator']), use_trace_approximation=bool(c['use_trace_approximation']))
+        lk = cls[c['kind']](M, C if c['cov'] is not None else None, mask_dict=masks, **kw)
+        assert abs(lk(S) - c['value']) <= 1e-8, name
+
+
+def test_bootstrap_dispersion_and_pickle(api):
+    rng = np.random.default_rng(1)
+    key = ('fd', None, 2, None)
+    M, S = api.Measurements(), api.Simulations()
+    M.append(name=key, data=rng.normal(size=(1, 48)), cov_data=np.full(48, 0.5), otype='HEALPix')
+    S.append(name=key, data=rng.normal(size=(12, 48)), otype='HEALPix')
+    lk = api.B200EnsembleLikelihood(M, compute_dispersion=True, n_bootstrap=20)
+    np.random.seed(3)
+    value, disp = lk(S)
+    assert np.isfinite(value) and disp > 0
+    assert abs(value - OK.ensemble_loglike(S[key].data, M[key].data, np.full(48, 0.5))) <= 1e-8
+    lk2 = pickle.loads(pickle.dumps(lk))
+    lk2.compute_dispersion = False
+    assert lk2(S) == value
+
+
+# ------------------------------------------------------------ template pipeline (TestSimulator + SimpleLikelihood)
+def test_template_pipeline_golden(api):
+    u = api.units
+
+    class FakeRandomTE(api.ThermalElectronDensityField):     # foreign plugin: no device descriptor
+        NAME = 'fake_rnd_TE'
+        STOCHASTIC_FIELD = True
+        DEPENDENCIES_LIST = []
+        PARAMETER_NAMES = ['param']
+
+        def compute_field(self, seed):
+            return np.ones(self.data_shape) * u.cm ** (-3)
+
+    fd_units = u.microgauss * u.cm ** -3
+    x = np.arange(5.0)
+    coords = {'x': x * u.kpc, 'y': np.zeros(5) * u.kpc, 'z': np.zeros(5) * u.kpc}
+    key = ('test', None, 'tab', None)
+    meas, covs = api.Measurements(), api.Covariances()
+    meas.append(name=key, data=np.ones((1, 5)) * fd_units, otype='tabular', coords=coords)
+    covs.append(name=key, cov_data=(np.ones(5) * 0.1) ** 2 * fd_units ** 2, otype='tabular')
+    likelihood = api.B200SimpleLikelihood(meas, covs)
+    grid = api.UniformGrid(box=[[0, 2 * np.pi] * u.kpc, [0, 0] * u.kpc, [0, 0] * u.kpc], resolution=[30, 1, 1])
+    simulator = api.B200TestSimulator(meas)
+
+    def loglike(cube):                                        # Pipeline._core_likelihood, pipeline.py:905-943
+        te = FakeRandomTE(grid, parameters={'param': cube[0]}, ensemble_size=2, ensemble_seeds=[11, 12])
+        b = api.ConstantMagneticField(grid, parameters={'Bx': cube[1] * u.microgauss, 'By': cube[2] * u.microgauss,
+                                                        'Bz': 3. * u.microgauss}, ensemble_size=2)
+        return likelihood(simulator([te, b]))
+
+    assert np.allclose(loglike(np.array([0.5, 10.5, 0.5])), -55.581767201053125, rtol=0, atol=1e-11)
+    # per-realisation contract through the base-class loop gives the same rows
+    te = FakeRandomTE(grid, parameters={'param': 1.0}, ensemble_size=2, ensemble_seeds=[11, 12])
+    b = api.ConstantMagneticField(grid, parameters={'Bx': 10.5 * u.microgauss, 'By': 0.5 * u.microgauss,
+                                                    'Bz': 3. * u.microgauss}, ensemble_size=2)
+    batched = simulator([te, b])[key].data
+    looped = api.Simulator.__call__(simulator, [te, b])[key].data
+    assert np.array_equal(batched, looped)
+    with pytest.raises(AssertionError):
+        simulator([b])                                        # missing required field
+
+
+# ------------------------------------------------------------ LOS simulator vs the oracle, through the API
+def _los_setup(api, nside=4, N=4, res=(20, 18, 12)):
+    u = api.units
+    m = 12 * nside * nside
+    grid = api.UniformGrid(box=[[-20, 20] * u.kpc, [-20, 20] * u.kpc, [-4, 4] * u.kpc], resolution=list(res))
+    rng = np.random.default_rng(0)
+    meas = api.Measurements()
+    keys = [('fd', None, nside, None), ('dm', None, nside, None), ('sync', 23.0, nside, 'I'),
+            ('sync', 23.0, nside, 'Q'), ('sync', 23.0, nside, 'U'), ('sync', 1.4, nside, 'PI'),
+            ('sync', 1.4, nside, 'PA')]
+    units = [u.rad / u.m ** 2, u.pc / u.cm ** 3, u.K, u.K, u.K, u.K, u.rad]
+    for k, un in zip(keys, units):
+        meas.append(name=k, data=rng.normal(size=(1, m)) * un, cov_data=np.ones(m) * un ** 2, otype='HEALPix')
+    seeds_b = [101, 102, 103, 104][:N]
+    fields = [
+        api.ConstantMagneticField(grid, parameters={'Bx': 0 * u.microgauss, 'By': 1 * u.microgauss,
+                                                    'Bz': 0 * u.microgauss}, ensemble_size=N),
+        api.NaiveGaussianMagneticField(grid, parameters={'a0': 0 * u.microgauss, 'b0': 2 * u.microgauss},
+                                       ensemble_size=N, ensemble_seeds=seeds_b),
+        api.ExponentialThermalElectrons(grid, parameters={'central_density': 0.01 * u.cm ** -3,
+                                                          'scale_radius': 3 * u.kpc, 'scale_height': 0.5 * u.kpc},
+                                        ensemble_size=N),
+        api.AnalyticCosmicRayElectrons(grid, parameters={'j0': 0.0217, 'r0': 5 * u.kpc, 'z0': 1 * u.kpc,
+                                                         'r_sun': 8.3 * u.kpc}, ensemble_size=N)]
+    return grid, meas, keys, fields, seeds_b
+
+
+def test_b200_simulator_matches_oracle(api):
+    nside, N, res = 4, 4, (20, 18, 12)
+    grid, meas, keys, fields, seeds_b = _los_setup(api, nside, N, res)
+    sim = api.B200Simulator(meas, radial_step=0.2)
+    sims = sim(fields)
+    assert isinstance(sims, api.Simulations) and set(sims.keys()) == set(keys)
+    og = OF.Grid([[-20, 20], [-20, 20], [-4, 4]], res)
+    stream = fields[1].device_descriptor()[2]
+    descs = [(OF.CONST_B, [0, 1, 0], 0), (OF.GAUSS_B, [0, 2], stream), (OF.EXP_NE, [0.01, 3, 0.5], 0),
+             (OF.CRE_ANALYTIC, [0.0217, 5, 1, 8.3], 0)]
+    of = OF.evaluate_fields(og, descs, seeds_b)
+    dirs = OH.pix2vec_ring(nside)
+    o23 = OL.integrate(og, OL.LosConfig(dr=0.2, nu_ghz=23.0), dirs, of['magnetic_field'],
+                       of['thermal_electron_density'], of['cosmic_ray_electron_density'])
+    o14 = OL.integrate(og, OL.LosConfig(dr=0.2, nu_ghz=1.4), dirs, of['magnetic_field'],
+                       of['thermal_electron_density'], of['cosmic_ray_electron_density'])
+    want = {keys[0]: o23['fd'], keys[1]: o23['dm'], keys[2]: o23['I'], keys[3]: o23['Q'], keys[4]: o23['U'],
+            keys[5]: np.sqrt(o14['Q'] ** 2 + o14['U'] ** 2), keys[6]: 0.5 * np.arctan2(o14['U'], o14['Q'])}
+    for k in keys:
+        got = sims[k].data
+        assert sims[k].shape == (N, 12 * nside ** 2) and sims[k].otype == 'HEALPix'
+        scale = np.abs(want[k]).max()
+        tol = 1e-9 if k[3] != 'PA' else 1e-7          # the angle amplifies Q,U rounding near |P| ~ 0
+        assert np.abs(got - want[k]).max() <= tol * scale, k
+    # per-realisation contract: base-class loop over host fields reproduces the batched rows
+    looped = api.Simulator.__call__(sim, fields)
+    for k in keys[:5]:
+        assert np.allclose(looped[k].data, sims[k].data, rtol=1e-9, atol=1e-12 * np.abs(sims[k].data).max()), k
+
+
+def test_full_drop_in_evaluation_and_units(api):
+    u = api.units
+    nside, N = 4, 4
+    grid, meas, keys, fields, _ = _los_setup(api, nside, N)
+    sim = api.B200Simulator(meas, radial_step=0.2)
+    lk = api.B200EnsembleLikelihood(meas)
+    sims = sim(fields)
+    value = lk(sims)
+    want = sum(OK.ensemble_loglike(sims[k].data, meas[k].data, np.ones(12 * nside ** 2)) for k in keys)
+    assert abs(value - want) <= 1e-8 * max(1.0, abs(want))
+    # measurements in other units: the simulator converts its maps (simulator.py:417-419)
+    meas2 = api.Measurements()
+    k = ('dm', None, nside, None)
+    meas2.append(name=k, data=np.ones((1, 192)) * (u.kpc / u.cm ** 3), otype='HEALPix')
+    s2 = api.B200Simulator(meas2, radial_step=0.2)(fields)
+    assert np.allclose(s2[k].data * 1e3, sims[k].data, rtol=1e-14)
+    # masked likelihood: masked keys are renamed (name, freq, n_kept, tag)
+    mask = api.Masks()
+    keep = (np.arange(192) % 3 != 0).astype(float).reshape(1, -1)
+    for key in keys:
+        mask.append(name=key, data=keep, otype='HEALPix')
+    lkm = api.B200EnsembleLikelihood(meas, mask_dict=mask)
+    b = keep[0].astype(bool)
+    want = sum(OK.ensemble_loglike(sims[key].data[:, b], meas[key].data[:, b], np.ones(int(b.sum()))) for key in keys)
+    assert abs(lkm(sims) - want) <= 1e-8 * max(1.0, abs(want))
+    # checkpointing: drop-ins survive pickling without device handles (io.py:25-75)
+    sim2, lk2 = pickle.loads(pickle.dumps(sim)), pickle.loads(pickle.dumps(lk))
+    assert lk2(sim2(fields)) == value
+    host_sims = pickle.loads(pickle.dumps(sims[keys[0]]))
+    assert np.array_equal(host_sims.data, sims[keys[0]].data)
+
+
+def test_gpu_fields_serve_host_consumers(api):
+    u = api.units
+    grid = api.UniformGrid(box=[[-15, 15] * u.kpc] * 3, resolution=[15, 15, 15])
+    f = api.ExponentialThermalElectrons(grid, parameters={'central_density': 1.0 * u.cm ** -3,
+                                                          'scale_radius': 3.3 * u.kpc, 'scale_height': 3.3 * u.kpc})
+    d = f.get_data()
+    want = [0.00189093, 0.00361981, 0.00289678, 0.0055453, 0.00289678, 0.0055453, 0.00473694, 0.00906791]
+    assert np.allclose(d.value[3:5, 3:5, 3:5].ravel(), want, rtol=0, atol=5e-9)     # tutorial_fields.ipynb:249-256
+    g = api.NaiveGaussianMagneticField(grid, parameters={'a0': 3 * u.microgauss, 'b0': 6 * u.microgauss},
+                                       ensemble_size=2, ensemble_seeds=[5, 6])
+    a, b = g.get_data(0), g.get_data(1)
+    assert a.shape == (15, 15, 15, 3) and not np.array_equal(a.value, b.value)
+    assert np.array_equal(g.get_data(0).value, a.value)
+    assert abs(a.value.mean() - 3) < 0.5 and abs(a.value.std() - 6) < 0.5
