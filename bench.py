@@ -261,18 +261,39 @@ def main():
     total_ms = t_start.elapsed_time(t_end)
     stage = np.array([[r[i].elapsed_time(r[i + 1]) for i in range(4)] for r in records]).mean(0)
 
-    # ---- end-to-end steps: host buffers in, host float out -------------------------------------------
-    seeds_h = torch.from_numpy(seeds.astype(np.int64)).pin_memory()
-    h2d = sum(meas_h[q].numel() * 8 + var_h[q].numel() * 8 for q in quantities) + seeds_h.numel() * 8
+    # ---- end-to-end steps: the plugin API a Pipeline calls (pipelines/pipeline.py:827-852, 905-943):
+    # new Field objects per evaluation, Simulator.__call__, Likelihood.__call__; measurements and
+    # variances start in HOST memory every step (device caches dropped), result is a host float
+    import imagine_b200.api as api
+    u = api.units
+    api_grid = api.UniformGrid(box=[[b[0], b[1]] * u.kpc for b in BOX], resolution=[G] * 3)
+    key_of = {'fd': ('fd', None, nside, None), 'dm': ('dm', None, nside, None),
+              'I': ('sync', 23.0, nside, 'I'), 'Q': ('sync', 23.0, nside, 'Q'), 'U': ('sync', 23.0, nside, 'U')}
+    unit_of = {'fd': u.rad / u.m ** 2, 'dm': u.pc / u.cm ** 3, 'I': u.K, 'Q': u.K, 'U': u.K}
+    api_meas = api.Measurements()
+    for q in quantities:
+        api_meas.append(name=key_of[q], data=meas_h[q].numpy().reshape(1, -1) * unit_of[q],
+                        cov_data=var_h[q].numpy() * unit_of[q] ** 2, otype='HEALPix')
+    api_sim = api.B200Simulator(api_meas, observer=LOS_KW['observer'], radial_step=LOS_KW['dr'],
+                                radial_max=LOS_KW['r_max'], cre_alpha=LOS_KW['alpha'], cre_E0=LOS_KW['e0_gev'],
+                                rank=rank, world=world)
+    api_lik = api.B200EnsembleLikelihood(api_meas)
+    seed_list = [int(v) for v in seeds]
+    h2d = sum(meas_h[q].numel() * 8 + var_h[q].numel() * 8 for q in quantities) + len(seed_list) * 8
 
     def e2e_step():
-        md = {q: meas_h[q].cuda(non_blocking=True) for q in quantities}
-        vd = {q: var_h[q].cuda(non_blocking=True) for q in quantities}
-        sd = seeds_h.cuda(non_blocking=True)                 # seeds travel with the field request
-        ev.simulate(descs, seeds_h.numpy().astype(np.uint64))
-        val = ev.loglike(ev.gather(), md, vd)                # D2H of the scalar happens inside
-        del sd
-        return float(val)
+        fields = [api.ExponentialThermalElectrons(api_grid, parameters={
+                      'central_density': 0.01 * u.cm ** -3, 'scale_radius': 3.0 * u.kpc,
+                      'scale_height': 0.1 * u.kpc}, ensemble_size=N),
+                  api.ConstantMagneticField(api_grid, parameters={
+                      'Bx': 0 * u.microgauss, 'By': 1 * u.microgauss, 'Bz': 0 * u.microgauss}, ensemble_size=N),
+                  api.NaiveGaussianMagneticField(api_grid, parameters={
+                      'a0': 0 * u.microgauss, 'b0': 2 * u.microgauss}, ensemble_size=N, ensemble_seeds=seed_list)]
+        if any(q in quantities for q in 'IQU'):
+            fields.append(api.AnalyticCosmicRayElectrons(api_grid, parameters={
+                'j0': 0.0217, 'r0': 5.0 * u.kpc, 'z0': 1.0 * u.kpc, 'r_sun': 8.3 * u.kpc}, ensemble_size=N))
+        api_lik._reset_device_state()                 # measurements/variances re-uploaded from host
+        return float(api_lik(api_sim(fields)))
 
     e2e_step()
     barrier()

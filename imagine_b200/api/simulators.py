@@ -26,7 +26,7 @@ from ._bases import Simulator, Simulations
 from .device_observable import DeviceObservable
 from .fields import descriptor_of, device_grid
 from .. import engine
-from ..hotpath import shard_bounds
+from ..hotpath import gather_rows, shard_bounds
 
 FIELD_UNITS = {'magnetic_field': u.microgauss, 'thermal_electron_density': u.cm ** -3}
 _NAMES = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
@@ -232,10 +232,7 @@ class B200Simulator(Simulator):
         for key in self.observables:
             block = maps[key]
             if self.world > 1:
-                import torch.distributed as dist
-                full = _torch().empty((N, block.shape[1]), dtype=block.dtype, device=block.device)
-                dist.all_gather_into_tensor(full, block.contiguous(), group=self.group)
-                block = full
+                block = gather_rows(block, N, self.group)
             unit = self.output_units.get(key) or self._units(key)
             sims.append(name=key, data=DeviceObservable(block, unit, self.output_coords[key],
                                                         self.output_type[key]),

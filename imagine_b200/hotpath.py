@@ -26,6 +26,21 @@ def shard_bounds(n_real, rank, world):
     return rank * per, (rank + 1) * per
 
 
+def gather_rows(local, n_real, group=None):
+    """
+    All-gather of per-rank row blocks [n_local, m] into the global ensemble [n_real, m], rows in
+    global realisation order.  Backend-agnostic (NCCL on device tensors, gloo on CPU tensors in
+    the host-logic tests); a single-rank call returns `local` itself.
+    """
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    full = torch.empty((n_real, local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(full, local.contiguous(), group=group)
+    return full
+
+
 class EnsembleEvaluator:
     def __init__(self, box, resolution, nside, los_settings, quantities=('fd', 'dm', 'I', 'Q', 'U'),
                  n_real=1, rank=0, world=1, b_stride=4, group=None):
