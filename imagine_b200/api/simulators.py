@@ -67,6 +67,8 @@ class _DeviceFieldEvaluator:
 
     def __init__(self, b_stride):
         self.b_stride = b_stride
+        self.effective_b_stride = 4 if b_stride == 16 else b_stride
+        self._bufs = {}
 
     def evaluate(self, fields, grid, lo, hi):
         torch = _torch()
@@ -84,14 +86,28 @@ class _DeviceFieldEvaluator:
                 row = len(seed_rows) - 1
             descs.append((d[0], d[1], d[2], row))
         seeds = np.stack(seed_rows) if seed_rows else np.zeros((1, n_local), dtype=np.uint64)
-        out = engine.field_eval(dg, descs, seeds, n_real=n_local, b_stride=self.b_stride) if descs else {}
+        b_stride = self.b_stride
+        if b_stride == 16 and any(f.type == 'magnetic_field' for f in foreign):
+            b_stride = 4              # host arrays are summed in the row-major padded layout
+        out = {}
+        if descs:
+            # device buffers persist across evaluations (a Pipeline calls this ~10^4 times)
+            shapes, b_stride = engine.field_shapes(dg, descs, n_local, b_stride)
+            for name, shape in shapes.items():
+                buf = self._bufs.get(name)
+                if buf is None or tuple(buf.shape) != shape:
+                    buf = torch.empty(shape, dtype=torch.float64, device='cuda')
+                    self._bufs[name] = buf
+                out[name] = buf
+            out = engine.field_eval(dg, descs, seeds, n_real=n_local, b_stride=b_stride, out=out)
+        self.effective_b_stride = b_stride if b_stride != 16 else 4
         # foreign plugins: host get_data -> upload -> device sum (simulator.py:166-178 semantics)
         for f in foreign:
             unit = FIELD_UNITS.get(f.type, f.units)
             rows = n_local if f.stochastic_field else 1
             host = np.stack([_host_values(f.get_data(lo + i), unit) for i in range(rows)])
             if f.type == 'magnetic_field':
-                dev = torch.zeros((rows, dg.ncell, self.b_stride), dtype=torch.float64, device='cuda')
+                dev = torch.zeros((rows, dg.ncell, self.effective_b_stride), dtype=torch.float64, device='cuda')
                 dev[:, :, :3] = torch.from_numpy(host.reshape(rows, dg.ncell, 3)).cuda()
             else:
                 dev = torch.from_numpy(host.reshape(rows, dg.ncell)).cuda()
@@ -121,7 +137,7 @@ class B200Simulator(Simulator):
     ALLOWED_GRID_TYPES = ['cartesian']
 
     def __init__(self, measurements, observer=(-8.3, 0.0, 0.006), radial_step=0.1, radial_max=30.0,
-                 cre_alpha=3.0, cre_beta=0.0, cre_theta=0.0, cre_E0=20.6, b_stride=4,
+                 cre_alpha=3.0, cre_beta=0.0, cre_theta=0.0, cre_E0=20.6, b_stride=16,
                  rank=0, world=1, group=None):
         super().__init__(measurements)
         self.los_kwargs = dict(observer=tuple(float(u.value_in(v, u.kpc)) for v in observer),
@@ -130,6 +146,7 @@ class B200Simulator(Simulator):
                                alpha=float(cre_alpha), beta=float(cre_beta), theta=float(cre_theta),
                                e0_gev=float(cre_E0))
         self.b_stride = int(b_stride)
+        self._evaluator = None
         self.rank, self.world, self.group = int(rank), int(world), group
         self._dirs = {}
         self._row_cache = (None, {})
@@ -226,7 +243,9 @@ class B200Simulator(Simulator):
         fields = _accepted_fields(self, field_list)
         N = self._ensemble_size
         lo, hi = shard_bounds(N, self.rank, self.world)
-        dg, dev_fields = _DeviceFieldEvaluator(self.b_stride).evaluate(fields, self.grid, lo, hi)
+        if self._evaluator is None:
+            self._evaluator = _DeviceFieldEvaluator(self.b_stride)
+        dg, dev_fields = self._evaluator.evaluate(fields, self.grid, lo, hi)
         maps = self._integrate(dg, dev_fields, hi - lo)
         sims = Simulations()
         for key in self.observables:
@@ -252,7 +271,7 @@ class B200Simulator(Simulator):
                     continue
                 host = _host_values(self.fields[name], FIELD_UNITS.get(name))
                 if name == 'magnetic_field':
-                    t = torch.zeros((1, dg.ncell, self.b_stride), dtype=torch.float64, device='cuda')
+                    t = torch.zeros((1, dg.ncell, 4), dtype=torch.float64, device='cuda')
                     t[:, :, :3] = torch.from_numpy(host.reshape(1, dg.ncell, 3)).cuda()
                 else:
                     t = torch.from_numpy(host.reshape(1, dg.ncell)).cuda()
@@ -265,6 +284,7 @@ class B200Simulator(Simulator):
     def __getstate__(self):
         state = dict(self.__dict__)
         state['_dirs'] = {}
+        state['_evaluator'] = None
         state['_row_cache'] = (None, {})
         state['group'] = None
         return state

@@ -89,6 +89,53 @@ __global__ void __launch_bounds__(256) field_b_kernel(const __grid_constant__ Fi
   }
 }
 
+// ---- magnetic field, realisation-interleaved layout (b_stride 16) ------------------------
+// out[group][cell][r4][4], group = r / 4, r4 = r % 4: the four realisations of a vertex share one
+// 128-byte line (what the LOS kernel's 4-lanes-per-sample gathers want).  Thread = (pair of
+// cells, realisation), r4 fastest, so a warp writes 2 KB contiguous.
+__global__ void __launch_bounds__(256) field_b_il4_kernel(const __grid_constant__ FieldArgs a,
+                                                          double* __restrict__ out) {
+  const long long npair = (a.g.ncell + 1) >> 1;
+  const long long n_groups = (a.rows + 3) >> 2;
+  const long long total = npair * n_groups * 4;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
+       w += (long long)gridDim.x * blockDim.x) {
+    const int r4 = (int)(w & 3);
+    const long long t_ = w >> 2;
+    const long long g = t_ / npair;
+    const long long q = t_ - g * npair;
+    const int r = (int)(g * 4 + r4);
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (r < a.rows) {
+      bool first = true;
+      for (int f = 0; f < a.nfields; ++f) {
+        double t[6];
+        if (a.kind[f] == IMB_FIELD_CONST_B) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) t[k] = a.p[f][k % 3];
+        } else {
+          const unsigned long long seed = a.seeds[(size_t)a.seed_row[f] * a.n_real + r];
+          const double mu = a.p[f][0], sigma = a.p[f][1];
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            double z0, z1;
+            philox_normal_pair(seed, a.stream[f], (unsigned long long)(3 * q + b), z0, z1);
+            t[2 * b] = __dadd_rn(__dmul_rn(z0, sigma), mu);
+            t[2 * b + 1] = __dadd_rn(__dmul_rn(z1, sigma), mu);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] = first ? t[k] : __dadd_rn(v[k], t[k]);
+        first = false;
+      }
+    }
+    const long long c0 = 2 * q;
+    double* o = out + ((g * a.g.ncell + c0) * 4 + r4) * 4;
+    *reinterpret_cast<double4*>(o) = make_double4(v[0], v[1], v[2], 0.0);
+    if (c0 + 1 < a.g.ncell) *reinterpret_cast<double4*>(o + 16) = make_double4(v[3], v[4], v[5], 0.0);
+  }
+}
+
 // ---- scalar fields (thermal electrons, cosmic-ray electrons): [rows, ncell] -----------
 __device__ __forceinline__ double scalar_model(const FieldArgs& a, int f, double x, double y,
                                                double z) {
@@ -322,7 +369,7 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
   DevGrid g;
   IMB_TRY(make_dev_grid(grid, &g));
   if (!fields || nfields < 0 || n_real < 1) return IMB_EINVAL;
-  if (out_B && b_stride != 3 && b_stride != 4) return IMB_EINVAL;
+  if (out_B && b_stride != 3 && b_stride != 4 && b_stride != 16) return IMB_EINVAL;
   for (int f = 0; f < nfields; ++f)
     if (field_type(fields[f].kind) < 0) return IMB_EINVAL;
 
@@ -370,7 +417,12 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
     const uintptr_t addr = reinterpret_cast<uintptr_t>(outs[type]);
     if (type == 0) {
       const long long row_elems = g.ncell * b_stride;
-      if (b_stride == 3) {
+      if (b_stride == 16) {
+        // realisation-interleaved: [ceil(rows/4), ncell, 4, 4]; only meaningful per realisation
+        if (need != n_real || addr % 32 != 0) return IMB_EINVAL;
+        const long long work4 = ((g.ncell + 1) / 2) * ((need + 3) / 4) * 4;
+        field_b_il4_kernel<<<grid_blocks(work4, 256, 8), 256, 0, stream>>>(a, outs[type]);
+      } else if (b_stride == 3) {
         const bool vec = (addr % 16 == 0) && (need == 1 || row_elems % 2 == 0);
         if (vec) field_b_kernel<3, true><<<blocks, 256, 0, stream>>>(a, outs[type]);
         else field_b_kernel<3, false><<<blocks, 256, 0, stream>>>(a, outs[type]);

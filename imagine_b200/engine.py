@@ -72,6 +72,25 @@ def field_rows(descs, n_real):
     return tuple(lib.imb_field_rows(arr, n, t, n_real) for t in range(3))
 
 
+FIELD_NAMES = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
+
+
+def field_shapes(grid, descs, n_real, b_stride=4):
+    """Buffer shapes `field_eval` will use/expect: {name: shape}, plus the effective b_stride."""
+    rows = field_rows(descs, n_real)
+    if b_stride == 16 and rows[0] != n_real:
+        b_stride = 4
+    shapes = {}
+    for t, name in enumerate(FIELD_NAMES):
+        if rows[t] == 0:
+            continue
+        if t == 0 and b_stride == 16:
+            shapes[name] = ((rows[0] + 3) // 4, grid.ncell, 4, 4)
+        else:
+            shapes[name] = (rows[t], grid.ncell, b_stride) if t == 0 else (rows[t], grid.ncell)
+    return shapes, b_stride
+
+
 def field_eval(grid, descs, seeds, n_real=None, b_stride=4, out=None):
     """
     Evaluate and sum all fields (imb_field_eval).  Returns dict with any of
@@ -91,10 +110,15 @@ def field_eval(grid, descs, seeds, n_real=None, b_stride=4, out=None):
     rows = field_rows(descs, n_real)
     names = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
     bufs = {}
+    if b_stride == 16 and rows[0] != n_real:
+        b_stride = 4          # interleaving realisations only makes sense for a stochastic B
     for t, name in enumerate(names):
         if rows[t] == 0:
             continue
-        shape = (rows[t], grid.ncell, b_stride) if t == 0 else (rows[t], grid.ncell)
+        if t == 0 and b_stride == 16:
+            shape = ((rows[0] + 3) // 4, grid.ncell, 4, 4)      # [group][cell][realisation%4][x,y,z,0]
+        else:
+            shape = (rows[t], grid.ncell, b_stride) if t == 0 else (rows[t], grid.ncell)
         if out is not None and name in out:
             buf = out[name]
             if tuple(buf.shape) != shape:
@@ -152,8 +176,10 @@ def los_integrate(grid, settings, dirs, B, ne=None, cre=None, n_real=1,
             else:
                 res[k] = torch.empty((n_real, m), dtype=torch.float64, device=B.device)
     cfg = settings.c_struct()
+    interleaved = B.dim() == 4                      # [group][cell][4][4] realisation-interleaved layout
     L.check(L.load().imb_los_integrate(
-        C.byref(grid.c), C.byref(cfg), L.ptr(dirs), m, L.ptr(B), B.shape[0], B.shape[-1],
+        C.byref(grid.c), C.byref(cfg), L.ptr(dirs), m, L.ptr(B),
+        n_real if interleaved else B.shape[0], 16 if interleaved else B.shape[-1],
         L.ptr(ne), 0 if ne is None else ne.shape[0], L.ptr(cre), 0 if cre is None else cre.shape[0],
         n_real, L.ptr(res.get('dm')), L.ptr(res.get('fd')), L.ptr(res.get('I')),
         L.ptr(res.get('Q')), L.ptr(res.get('U')), L.stream_ptr()))

@@ -43,7 +43,7 @@ def gather_rows(local, n_real, group=None):
 
 class EnsembleEvaluator:
     def __init__(self, box, resolution, nside, los_settings, quantities=('fd', 'dm', 'I', 'Q', 'U'),
-                 n_real=1, rank=0, world=1, b_stride=4, group=None):
+                 n_real=1, rank=0, world=1, b_stride=16, group=None):
         import torch
         self.torch = torch
         self.grid = engine.DeviceGrid(box, resolution)
@@ -73,13 +73,9 @@ class EnsembleEvaluator:
         seeds = np.atleast_2d(np.asarray(seeds, dtype=np.uint64))
         if seeds.shape[1] != self.n_real:
             raise ValueError('need one seed per (global) realisation')
-        rows = engine.field_rows(descs, self.n_local)
-        names = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
+        shapes, _ = engine.field_shapes(self.grid, descs, self.n_local, self.b_stride)
         out = {}
-        for t, name in enumerate(names):
-            if rows[t] == 0:
-                continue
-            shape = (rows[t], self.grid.ncell, self.b_stride) if t == 0 else (rows[t], self.grid.ncell)
+        for name, shape in shapes.items():
             buf = self._field_bufs.get(name)
             if buf is None or tuple(buf.shape) != shape:
                 buf = self.torch.empty(shape, dtype=self.torch.float64, device=self.dirs.device)

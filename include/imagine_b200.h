@@ -111,7 +111,11 @@ int64_t imb_launch_count(void);
  *              seed list; fields[f].seed_row selects the row of a stochastic field
  *   out_B      [rows_B, ncell, b_stride]  b_stride = 3 (reference layout, component
  *              innermost) or 4 (padded, 4th component = 0); rows_* is n_real if a
- *              stochastic field of that type is present, else 1 (IMB_EINVAL otherwise)
+ *              stochastic field of that type is present, else 1 (IMB_EINVAL otherwise).
+ *              b_stride = 16 selects the realisation-interleaved layout
+ *              [ceil(n_real/4), ncell, 4 realisations, 4]: realisation r lives in group r/4,
+ *              slot r%4, so the four realisations of a vertex share one 128-byte line (the
+ *              layout the LOS kernel gathers fastest from); needs rows_B == n_real.
  *   out_ne     [rows_ne, ncell]     out_cre  [rows_cre, ncell]
  * A NULL output skips that field type.  Asynchronous.
  */
@@ -145,7 +149,8 @@ int imb_healpix_ring_dirs(int nside, double* dirs, void* stream);
  * Integrates all realisations along the directions `dirs` [m,3] (unit vectors in the
  * Galactic-centric frame).  Replaces Hammurabi.simulate + the hammurabiX run behind it
  * (simulators/hammurabi.py:193-227); numeric definition: oracle/los.py.
- *   B   [rows_B, ncell, b_stride]   ne [rows_ne, ncell] or NULL   cre [rows_cre, ncell] or NULL
+ *   B   [rows_B, ncell, b_stride] (b_stride 3 | 4), or the interleaved layout of
+ *       imb_field_eval (b_stride 16);   ne [rows_ne, ncell] or NULL   cre [rows_cre, ncell] or NULL
  *   out_dm, out_fd, out_I, out_Q, out_U  each [n_real, m] or NULL
  * fd/dm need ne; I/Q/U need cre (IMB_EINVAL otherwise).  Asynchronous.
  */

@@ -41,3 +41,14 @@ def oracle_value(case):
     if case['kind'] == 'simple':
         return L.simple_loglike(sims, meas, cov)
     raise ValueError(case['kind'])
+
+
+def b_to_reference_layout(B, n_real, grid_shape):
+    """Device B buffer (b_stride 3 | 4 | interleaved-16) -> NumPy [rows, nx, ny, nz, 3]."""
+    a = B.cpu().numpy()
+    if a.ndim == 4:                                   # [group][cell][realisation % 4][x,y,z,0]
+        g, ncell = a.shape[0], a.shape[1]
+        assert (a[..., 3] == 0.0).all()
+        a = a.transpose(0, 2, 1, 3).reshape(g * 4, ncell, 4)[:n_real]
+    rows = a.shape[0]
+    return a.reshape(rows, *grid_shape, a.shape[-1])[..., :3]

@@ -7,6 +7,7 @@ pytestmark = pytest.mark.gpu
 from oracle import fields as OF          # noqa: E402
 from oracle import healpix as OH         # noqa: E402
 from oracle import los as OL             # noqa: E402
+from tests.helpers import b_to_reference_layout   # noqa: E402
 
 BOX = [[-20, 20], [-20, 20], [-4, 4]]
 KEYS = ('dm', 'fd', 'I', 'Q', 'U')
@@ -34,7 +35,7 @@ def _run(eng, res, descs, seeds, nside, bs, cfg_kw, want=KEYS, dirs=None):
     torch.cuda.synchronize()
     og = OF.Grid(BOX, res)
     # identical realisations for the oracle: the GPU-generated grids themselves (north_star)
-    B = f['magnetic_field'].cpu().numpy().reshape(-1, *og.shape, bs)[..., :3]
+    B = b_to_reference_layout(f['magnetic_field'], N, og.shape)
     ne = f.get('thermal_electron_density')
     cre = f.get('cosmic_ray_electron_density')
     ne = None if ne is None else ne.cpu().numpy().reshape(-1, *og.shape)
@@ -58,16 +59,37 @@ DESCS = [(OF.CONST_B, [0.0, 1.0, 0.0], 0), (OF.GAUSS_B, [0.0, 2.0], 1),
          (OF.EXP_NE, [0.01, 3.0, 0.1], 2), (OF.CRE_ANALYTIC, [0.0217, 5.0, 1.0, 8.3], 3)]
 
 
-@pytest.mark.parametrize('bs', [3, 4])
-@pytest.mark.parametrize('N', [1, 2, 3, 5, 8])
+@pytest.mark.parametrize('bs', [3, 4, 16])
+@pytest.mark.parametrize('N', [1, 2, 3, 5, 8, 17])
 def test_all_observables_match_oracle(eng, bs, N):
     maps, omaps = _run(eng, [20, 18, 12], DESCS, list(range(50, 50 + N)), 4, bs, dict(dr=0.2))
     _check(maps, omaps)
 
 
-def test_nside16_grid32_23ghz(eng):
-    maps, omaps = _run(eng, [32, 32, 16], DESCS, [7, 8, 9, 10], 16, 4, dict(dr=0.1))
+@pytest.mark.parametrize('bs', [4, 16])
+def test_nside16_grid32_23ghz(eng, bs):
+    maps, omaps = _run(eng, [32, 32, 16], DESCS, [7, 8, 9, 10, 11, 12], 16, bs, dict(dr=0.1))
     _check(maps, omaps)
+
+
+def test_interleaved_layout_variants(eng):
+    """b_stride 16 through every kernel variant: Faraday only, sync only, variable index, random n_e."""
+    maps, omaps = _run(eng, [20, 18, 12], DESCS[:3], [1, 2, 3, 4, 5], 4, 16, dict(dr=0.2), want=('dm', 'fd'))
+    _check(maps, omaps, ('dm', 'fd'))
+    d = [DESCS[0], DESCS[1], DESCS[3]]
+    maps, omaps = _run(eng, [20, 18, 12], d, [1, 2, 3, 4, 5, 6, 7], 4, 16, dict(dr=0.2), want=('I', 'Q', 'U'))
+    _check(maps, omaps, ('I', 'Q', 'U'))
+    maps, omaps = _run(eng, [20, 18, 12], DESCS, list(range(1, 10)), 4, 16,
+                       dict(dr=0.2, alpha=2.7, beta=0.02, theta=-0.05, nu_ghz=2.3))
+    _check(maps, omaps)
+    descs = DESCS[:2] + [(OF.RANDOM_NE, [0.02, 0.01, 0.0], 4), DESCS[3]]
+    maps, omaps = _run(eng, [16, 16, 8], descs, [1, 2, 3, 4, 5, 6], 4, 16, dict(dr=0.2))
+    _check(maps, omaps)
+    # the layouts agree with each other bit for bit on the fields and to rounding on the maps
+    a, _ = _run(eng, [20, 18, 12], DESCS, [1, 2, 3, 4, 5], 4, 4, dict(dr=0.2))
+    b, _ = _run(eng, [20, 18, 12], DESCS, [1, 2, 3, 4, 5], 4, 16, dict(dr=0.2))
+    for k in KEYS:
+        assert np.allclose(a[k], b[k], rtol=1e-11, atol=1e-13 * np.abs(a[k]).max()), k
 
 
 def test_low_frequency_strong_faraday_rotation(eng):
