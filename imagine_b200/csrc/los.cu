@@ -8,6 +8,7 @@
 // warp inclusive scan per 32-sample chunk plus a carried prefix; the ray sums finish with a
 // warp-shuffle tree.  Numeric definition: oracle/los.py (the reference delegates this
 // stage to hammurabiX, simulators/hammurabi.py:193-227).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace imb {
@@ -240,8 +241,8 @@ __global__ void __launch_bounds__(256) los_kernel(const __grid_constant__ LosArg
 // The four lanes of a sample read the four 32-byte sectors of ONE 128-byte line per corner: a
 // 256-bit gather instruction touches <= 8 lines (4 sectors per L1 wavefront) instead of up to 32
 // with one line per lane in the row-major layouts.
-template <bool HAS_NE, bool HAS_CRE, bool VAR_P, int NG>
-__global__ void __launch_bounds__(256) los_il4_kernel(const __grid_constant__ LosArgs a) {
+template <bool HAS_NE, bool HAS_CRE, bool VAR_P, int NG, int MINB>
+__global__ void __launch_bounds__(256, MINB) los_il4_kernel(const __grid_constant__ LosArgs a) {
   const int lane = threadIdx.x & 31;
   const int slot = lane >> 2, r4 = lane & 3;
   const int pix = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -414,11 +415,16 @@ template <bool HAS_NE, bool HAS_CRE, bool VAR_P>
 static void launch_il4(const LosArgs& a, cudaStream_t s) {
   const int warps = 8;
   const int n_groups = (a.n_real + 3) / 4;
-  const int ng = n_groups >= 4 ? 4 : (n_groups >= 2 ? 2 : 1);
+  int ng = n_groups >= 4 ? 4 : (n_groups >= 2 ? 2 : 1);
+  int minb = 2;
+  if (const char* e = getenv("IMB_LOS_NG")) ng = atoi(e);
+  if (const char* e = getenv("IMB_LOS_MINB")) minb = atoi(e);
   dim3 grid((a.m + warps - 1) / warps, (n_groups + ng - 1) / ng);
-  if (ng == 4) los_il4_kernel<HAS_NE, HAS_CRE, VAR_P, 4><<<grid, 256, 0, s>>>(a);
-  else if (ng == 2) los_il4_kernel<HAS_NE, HAS_CRE, VAR_P, 2><<<grid, 256, 0, s>>>(a);
-  else los_il4_kernel<HAS_NE, HAS_CRE, VAR_P, 1><<<grid, 256, 0, s>>>(a);
+#define IMB_IL4(NG_, MB_) los_il4_kernel<HAS_NE, HAS_CRE, VAR_P, NG_, MB_><<<grid, 256, 0, s>>>(a)
+  if (ng == 4) { if (minb >= 3) IMB_IL4(4, 3); else IMB_IL4(4, 2); }
+  else if (ng == 2) { if (minb >= 4) IMB_IL4(2, 4); else if (minb == 3) IMB_IL4(2, 3); else IMB_IL4(2, 2); }
+  else { if (minb >= 4) IMB_IL4(1, 4); else if (minb == 3) IMB_IL4(1, 3); else IMB_IL4(1, 2); }
+#undef IMB_IL4
 }
 
 template <bool HAS_NE, bool HAS_CRE, bool VAR_P, int RT>
