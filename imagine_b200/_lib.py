@@ -71,6 +71,8 @@ _SIGNATURES = {
     'imb_mcov': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_double), _P]),
     'imb_loglike_ensemble': (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int32), _P]),
+    'imb_loglike_ensemble_batch': (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_int,
+                                             C.POINTER(C.c_double), C.POINTER(C.c_int32), _P]),
     'imb_loglike_ensemble_diagonal': (C.c_int, [_P, C.c_int, C.c_int, _P, _P,
                                                 C.POINTER(C.c_double), _P]),
     'imb_loglike_simple': (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int,

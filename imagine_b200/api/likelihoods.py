@@ -142,12 +142,29 @@ class B200EnsembleLikelihood(_DeviceLikelihoodMixin, Likelihood):
         assert isinstance(simulations_dict, Simulations)
         assert set(simulations_dict.keys()).issubset(self._measurement_dict.keys())
         assert set(simulations_dict.keys()).issubset(self._covariance_dict.keys())
+        # keys that may take the Gram route are evaluated in batches of identical [N, m]
+        # (one launch sequence + one read-back per batch); the others go one by one
+        names = list(simulations_dict.keys())
+        values, batches = {}, {}
+        gram_ok = (self.estimator in ('oas', 'empirical') and not self.use_trace_approximation
+                   and self.route in ('auto', 'gram'))
+        for name in names:
+            block = self._block(simulations_dict[name])
+            cov = self._covariance(name)
+            if gram_ok and cov.dim() == 1:
+                batches.setdefault(tuple(block.shape), []).append((name, block, cov))
+            else:
+                values[name] = engine.loglike_ensemble(
+                    block, self._measured(name), cov, estimator=self.estimator, route=self.route,
+                    use_trace_approximation=self.use_trace_approximation)
+        for items in batches.values():
+            vals = engine.loglike_ensemble_batch([b for _, b, _ in items],
+                                                 [self._measured(n) for n, _, _ in items],
+                                                 [c for _, _, c in items], estimator=self.estimator)
+            values.update({n: v for (n, _, _), v in zip(items, vals)})
         total = 0.
-        for name in simulations_dict:
-            total += engine.loglike_ensemble(
-                self._block(simulations_dict[name]), self._measured(name), self._covariance(name),
-                estimator=self.estimator, route=self.route,
-                use_trace_approximation=self.use_trace_approximation)
+        for name in names:                       # summed in dictionary order, like the reference
+            total += values[name]
         return total
 
 

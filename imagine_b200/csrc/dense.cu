@@ -12,44 +12,6 @@
 
 namespace imb {
 
-constexpr int TB = 64;       // output tile edge / Cholesky panel width
-constexpr int KC = 16;       // k-chunk staged in shared memory
-constexpr int LDS_ = TB + 4; // smem leading dimension: conflict-free DMMA fragment loads
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-// One 64x64 tile of acc = A * B^T over k in [0, K): warp w owns rows 8w..8w+7, all 8 column
-// blocks.  Operand element getters are functors so the same core serves SYRK and Cholesky.
-template <typename LoadA, typename LoadB>
-__device__ __forceinline__ void tile_mma(int K, LoadA loadA, LoadB loadB, double (&acc)[8][2],
-                                         double (*sA)[LDS_], double (*sB)[LDS_]) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int fr = lane >> 2, fk = lane & 3;
-  for (int k0 = 0; k0 < K; k0 += KC) {
-    for (int e = threadIdx.x; e < TB * KC; e += 256) {
-      int i, k;
-      loadA.index(e, i, k);
-      sA[k][i] = (k0 + k < K) ? loadA(i, k0 + k) : 0.0;
-      loadB.index(e, i, k);
-      sB[k][i] = (k0 + k < K) ? loadB(i, k0 + k) : 0.0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < KC; kk += 4) {
-      const double a = sA[kk + fk][warp * 8 + fr];
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb) {
-        const double b = sB[kk + fk][nb * 8 + fr];
-        dmma884(acc[nb][0], acc[nb][1], a, b);
-      }
-    }
-    __syncthreads();
-  }
-}
-
 // ---- build A = M + cov_est(sims) --------------------------------------------------------
 // operand(i,k) = X[k*m + i0+i] - mean[i0+i]  (i contiguous)
 struct CenteredOperand {

@@ -500,7 +500,7 @@ int imb_loglike_ensemble(const double* sims, int N, int m, const double* meas, c
   if (out_info) out_info[0] = out_info[1] = 0;
   if ((route == IMB_ROUTE_AUTO || route == IMB_ROUTE_GRAM) && gram_legal) {
     int fallback = 0;
-    IMB_TRY(loglike_gram(sims, N, m, meas, cov, estimator, out_loglike, out_info, &fallback, s));
+    IMB_TRY(loglike_gram_batch(1, &sims, N, m, &meas, &cov, estimator, out_loglike, out_info, &fallback, s));
     if (!fallback) return IMB_OK;
     if (route == IMB_ROUTE_GRAM) return IMB_OK;   // caller insisted; info[1] != 0 flags it
   }

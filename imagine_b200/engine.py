@@ -260,6 +260,29 @@ def loglike_ensemble(sims, meas, cov, estimator='oas', route='auto',
     return (out.value, (info[0], info[1])) if return_info else out.value
 
 
+def loglike_ensemble_batch(sims, meas, var, estimator='oas', return_info=False):
+    """
+    Sum-ready per-key values of EnsembleLikelihood for K observables of identical shape with
+    diagonal measurement covariances (imb_loglike_ensemble_batch): lists of tensors in, list of
+    floats out, one device synchronisation.
+    """
+    L.init()
+    K = len(sims)
+    sims = [_f64(t, 'sims') for t in sims]
+    meas = [_f64(t, 'meas').reshape(-1) for t in meas]
+    var = [_f64(t, 'var').reshape(-1) for t in var]
+    N, m = sims[0].shape
+    for s_, y_, v_ in zip(sims, meas, var):
+        if tuple(s_.shape) != (N, m) or y_.numel() != m or v_.numel() != m:
+            raise ValueError('batched keys must share one [N, m] shape')
+    arr = lambda ts: (C.c_void_p * K)(*[t.data_ptr() for t in ts])
+    out, info = (C.c_double * K)(), (C.c_int32 * (2 * K))()
+    L.check(L.load().imb_loglike_ensemble_batch(K, arr(sims), N, m, arr(meas), arr(var), _EST[estimator],
+                                                out, info, L.stream_ptr()))
+    vals = [out[k] for k in range(K)]
+    return (vals, [(info[2 * k], info[2 * k + 1]) for k in range(K)]) if return_info else vals
+
+
 def loglike_ensemble_diagonal(sims, meas, var):
     L.init()
     sims, meas, var = _f64(sims, 'sims'), _f64(meas, 'meas').reshape(-1), _f64(var, 'var')

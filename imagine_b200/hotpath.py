@@ -109,9 +109,12 @@ class EnsembleEvaluator:
     # -- stage 3 -------------------------------------------------------------------------------
     def loglike(self, maps, meas, var, estimator='oas'):
         """Sum over observables of EnsembleLikelihood's per-key term (diagonal measurement cov)."""
+        qs = self.quantities
+        vals = engine.loglike_ensemble_batch([maps[q] for q in qs], [meas[q] for q in qs],
+                                             [var[q] for q in qs], estimator=estimator)
         total = 0.0
-        for q in self.quantities:
-            total += engine.loglike_ensemble(maps[q], meas[q], var[q], estimator=estimator)
+        for v in vals:                      # same left-to-right sum as the reference's loop over keys
+            total += v
         return total
 
     def evaluate(self, descs, seeds, meas, var, estimator='oas'):

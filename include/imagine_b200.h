@@ -196,6 +196,18 @@ int imb_loglike_ensemble(const double* sims, int N, int m, const double* meas,
                          int use_trace_approximation,
                          double* out_loglike, int32_t* out_info, void* stream);
 
+/*
+ * The loop over observables of EnsembleLikelihood.call (ensemble_likelihood.py:86-105) in one
+ * batched pass: K keys with the same [N, m], diagonal measurement covariance, estimator
+ * EMPIRICAL or OAS, Gram route (a key whose shrunk diagonal is not positive falls back to the
+ * dense LU route on its own).  sims/meas/var are HOST arrays of K DEVICE pointers;
+ * out_loglike HOST [K]; out_info HOST [2K] or NULL.  One synchronisation for all keys.
+ */
+int imb_loglike_ensemble_batch(int K, const double* const* sims, int N, int m,
+                               const double* const* meas, const double* const* var,
+                               int estimator, double* out_loglike, int32_t* out_info,
+                               void* stream);
+
 /* EnsembleLikelihoodDiagonal.call (likelihoods/ensemble_likelihood.py:137-173);
  * var [m] = diagonal of the measurement covariance.  Synchronises. */
 int imb_loglike_ensemble_diagonal(const double* sims, int N, int m, const double* meas,

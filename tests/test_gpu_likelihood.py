@@ -191,3 +191,36 @@ def test_shape_errors(eng):
     with pytest.raises(ValueError):
         eng.loglike_ensemble(_dev(np.ones((2, 5))), _dev(np.ones(5)), _dev(np.ones(5)), estimator='diagonal',
                              route='gram')
+
+
+@pytest.mark.parametrize('N,m,K', [(6, 48, 3), (64, 3072, 5), (17, 1001, 2), (130, 400, 2), (200, 517, 1)])
+def test_batched_gram_route_matches_per_key_oracle(eng, N, m, K):
+    """imb_loglike_ensemble_batch == the per-key values (any N, incl. N > 64 blocks and N > 158 global path)."""
+    rng = np.random.default_rng(N + m + K)
+    sims = [rng.normal(size=(N, m)) * (k + 1) + rng.normal(size=m) for k in range(K)]
+    meas = [rng.normal(size=m) for _ in range(K)]
+    var = [rng.uniform(0.3, 1.2, size=m) for _ in range(K)]
+    for est in ('oas', 'empirical'):
+        got, info = eng.loglike_ensemble_batch([_dev(s) for s in sims], [_dev(y) for y in meas],
+                                               [_dev(v) for v in var], estimator=est, return_info=True)
+        for k in range(K):
+            want = OK.ensemble_loglike_gram(sims[k], meas[k], var[k], estimator=est)
+            assert abs(got[k] - want) <= 1e-8 * max(1.0, abs(want) * 1e-4), (k, got[k], want)
+            assert info[k][0] & 1
+            single = eng.loglike_ensemble(_dev(sims[k]), _dev(meas[k]), _dev(var[k]), estimator=est)
+            assert single == got[k]                       # batching does not change a key's value
+
+
+def test_batched_route_falls_back_per_key_on_nonpositive_variance(eng):
+    rng = np.random.default_rng(4)
+    N, m = 5, 24
+    sims = [rng.normal(size=(N, m)) for _ in range(2)]
+    meas = [rng.normal(size=m) for _ in range(2)]
+    var = [rng.uniform(0.5, 1.0, size=m), rng.uniform(0.5, 1.0, size=m)]
+    var[1][3] = -2.0                                      # negative "variance": reference LU handles it
+    got, info = eng.loglike_ensemble_batch([_dev(s) for s in sims], [_dev(y) for y in meas],
+                                           [_dev(v) for v in var], return_info=True)
+    assert info[0][0] & 1 and info[1][0] & 8
+    for k in range(2):
+        want = OK.ensemble_loglike(sims[k], meas[k], var[k])
+        assert abs(got[k] - want) <= 1e-8 * max(1.0, abs(want))
