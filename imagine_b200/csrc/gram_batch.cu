@@ -18,7 +18,7 @@
 namespace imb {
 
 constexpr int KMAX = 16;           // observables per batch launch
-constexpr int GSLICES = 32;        // column slices of the Gram GEMM (fixed => fixed summation order)
+constexpr int GCOLS = 256;         // columns per Gram slice (fixed => summation order depends on m only)
 
 struct BatchPtrs {
   const double* sims[KMAX];
@@ -46,20 +46,8 @@ __global__ void __launch_bounds__(256) bg_colmean_kernel(const __grid_constant__
   ws.k[key].diff[i] = __dsub_rn(p.meas[key][i], mu);
 }
 
-// operand(i, k) = (X[(r0+i)*m + c0+k] - mean[c0+k]) * (w ? w[c0+k] : 1), k contiguous
-struct GramOperand {
-  const double* X; const double* mean; const double* w;
-  int m, N, r0, c0, c_end;
-  __device__ __forceinline__ void index(int e, int& i, int& k) const { k = e & (KC - 1); i = e >> 4; }
-  __device__ __forceinline__ double operator()(int i, int k) const {
-    const int row = r0 + i, col = c0 + k;
-    if (row >= N || col >= c_end) return 0.0;
-    double v = X[(size_t)row * m + col] - mean[col];
-    if (w) v *= w[col];
-    return v;
-  }
-};
-
+// acc = A * B^T over the slice columns; when the row blocks coincide (always for N <= 64) the
+// tile is staged once and written to both operand buffers (weighted copy for A).
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(256) bg_gram_kernel(const __grid_constant__ BatchPtrs p,
                                                       const __grid_constant__ BatchWs ws, int N, int m,
@@ -72,15 +60,39 @@ __global__ void __launch_bounds__(256) bg_gram_kernel(const __grid_constant__ Ba
   const int bi = blockIdx.y / nb, bj = blockIdx.y % nb;
   const int c0 = blockIdx.x * cols_per_slice;
   const int c_end = min(m, c0 + cols_per_slice);
+  const double* __restrict__ X = p.sims[key];
+  const double* __restrict__ mean = kw.mean;
+  const double* __restrict__ w = kw.w;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
   double acc[8][2];
 #pragma unroll
   for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = 0.0;
-  if (c0 < c_end) {
-    GramOperand A{p.sims[key], kw.mean, WEIGHTED ? kw.w : nullptr, m, N, bi * TB, c0, c_end};
-    GramOperand B{p.sims[key], kw.mean, nullptr, m, N, bj * TB, c0, c_end};
-    tile_mma(c_end - c0, A, B, acc, sA, sB);
+  for (int k0 = c0; k0 < c_end; k0 += KC) {
+    for (int e = threadIdx.x; e < TB * KC; e += 256) {
+      const int k = e & (KC - 1), i = e >> 4;
+      const int col = k0 + k;
+      double a = 0.0, b = 0.0;
+      if (col < c_end) {
+        const double mu = mean[col];
+        const int ra = bi * TB + i, rb = bj * TB + i;
+        if (rb < N) b = X[(size_t)rb * m + col] - mu;
+        if (bi == bj) a = b;
+        else if (ra < N) a = X[(size_t)ra * m + col] - mu;
+        if (WEIGHTED) a *= w[col];
+      }
+      sA[k][i] = a;
+      sB[k][i] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC; kk += 4) {
+      const double a = sA[kk + fk][warp * 8 + fr];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dmma884(acc[q][0], acc[q][1], a, sB[kk + fk][q * 8 + fr]);
+    }
+    __syncthreads();
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = bi * TB + warp * 8 + (lane >> 2);
   if (i >= N) return;
   double* out = kw.partial + (size_t)blockIdx.x * N * N;
@@ -176,22 +188,26 @@ __global__ void __launch_bounds__(256) bg_wdot_kernel(const __grid_constant__ Ba
 }
 
 // One block per key.  T = [K; y^T] is (N+1) x N (leading dimension ldt) in shared or global memory.
+// Right-looking Cholesky with ONE barrier per column: the update of column block k reads the
+// unscaled column k and divides by the pivot, while the scaled column is written to a separate
+// array L (so no thread overwrites what another still reads).
 __global__ void __launch_bounds__(256) bg_finish_kernel(const __grid_constant__ BatchWs ws, int N,
                                                         int slices, int dparts, int use_smem, int ldt) {
   extern __shared__ double smT[];
+  __shared__ double red[32];
   __shared__ double sh[4];
   __shared__ int bad;
   const KeyWs& kw = ws.k[blockIdx.x];
   LikeScalars* sc = kw.sc;
   const int tid = threadIdx.x, nt = blockDim.x;
   double* T = use_smem ? smT : kw.partial;         // partial is free again: reuse as global scratch
-  if (tid == 0) {
-    double a = 0, b = 0, c = 0, d = 0;
-    for (int k = 0; k < dparts; ++k) {
+  {
+    double a = 0, b = 0, c = 0, d = 0;              // fixed order: thread t takes parts t, t+nt, ...
+    for (int k = tid; k < dparts; k += nt) {
       a += kw.dpart[4 * k]; b += kw.dpart[4 * k + 1]; c += kw.dpart[4 * k + 2]; d += kw.dpart[4 * k + 3];
     }
-    sh[0] = a; sh[1] = b; sh[2] = c; sh[3] = d;
-    bad = 0;
+    a = block_sum(a, red); b = block_sum(b, red); c = block_sum(c, red); d = block_sum(d, red);
+    if (tid == 0) { sh[0] = a; sh[1] = b; sh[2] = c; sh[3] = d; bad = 0; }
   }
   const double c = sc->c;
   for (int e = tid; e < N * N; e += nt) {
@@ -204,31 +220,26 @@ __global__ void __launch_bounds__(256) bg_finish_kernel(const __grid_constant__ 
     T[(size_t)N * ldt + r] = s;
   }
   __syncthreads();
-  // right-looking Cholesky of the lower triangle; row N (the rhs) is updated like any other row
+  // after step k: column k of T holds UNSCALED values a_ik (i >= k); pivot = a_kk
+  double ld = 0.0, zz = 0.0;
   for (int k = 0; k < N; ++k) {
-    if (tid == 0) {
-      const double pv = T[(size_t)k * ldt + k];
-      if (!(pv > 0.0) && bad == 0) bad = k + 1;
-      T[(size_t)k * ldt + k] = sqrt(pv);
-    }
-    __syncthreads();
-    const double lkk = T[(size_t)k * ldt + k];
-    for (int i = k + 1 + tid; i <= N; i += nt) T[(size_t)i * ldt + k] /= lkk;
-    __syncthreads();
+    const double pv = T[(size_t)k * ldt + k];
+    if (tid == 0 && !(pv > 0.0) && bad == 0) bad = k + 1;
+    const double inv = 1.0 / pv;
     const int rem = N - k;                       // rows k+1 .. N, columns k+1 .. N-1
     for (int e = tid; e < rem * (rem - 1); e += nt) {
       const int i = k + 1 + e / (rem - 1), j = k + 1 + e % (rem - 1);
-      if (j <= i && j < N) T[(size_t)i * ldt + j] -= T[(size_t)i * ldt + k] * T[(size_t)j * ldt + k];
+      if (j <= i && j < N)
+        T[(size_t)i * ldt + j] -= T[(size_t)i * ldt + k] * T[(size_t)j * ldt + k] * inv;
+    }
+    if (tid == 0) {
+      ld += log(pv);                             // log|K| = sum log(pivot)
+      const double z = T[(size_t)N * ldt + k];   // z_k = a_Nk / sqrt(pivot)
+      zz += z * z * inv;
     }
     __syncthreads();
   }
   if (tid == 0) {
-    double ld = 0.0, zz = 0.0;
-    for (int k = 0; k < N; ++k) {
-      ld += 2.0 * log(T[(size_t)k * ldt + k]);
-      const double z = T[(size_t)N * ldt + k];
-      zz += z * z;
-    }
     const double quad = sh[0] - c * zz;
     const double logdet = sh[1] + ld;
     const double sign = (((long long)sh[3]) & 1) ? -1.0 : 1.0;
@@ -245,8 +256,7 @@ static int run_batch(int K, const double* const* sims, int N, int m, const doubl
                      const double* const* var, int estimator, LikeScalars* h_out, cudaStream_t s) {
   const int nn = N * N;
   const int dparts = grid_blocks(m, 256, 1);
-  int cps = (m + GSLICES - 1) / GSLICES;
-  cps = (cps + KC - 1) / KC * KC;
+  const int cps = GCOLS;
   const int slices = (m + cps - 1) / cps;
   const size_t tn = (size_t)(N + 1) * (N + 1);
   const size_t partial_elems = (size_t)slices * nn > tn ? (size_t)slices * nn : tn;
