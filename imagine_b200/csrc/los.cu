@@ -421,8 +421,8 @@ static void launch_il4(const LosArgs& a, cudaStream_t s) {
   if (const char* e = getenv("IMB_LOS_MINB")) minb = atoi(e);
   dim3 grid((a.m + warps - 1) / warps, (n_groups + ng - 1) / ng);
 #define IMB_IL4(NG_, MB_) los_il4_kernel<HAS_NE, HAS_CRE, VAR_P, NG_, MB_><<<grid, 256, 0, s>>>(a)
-  if (ng == 4) { if (minb >= 3) IMB_IL4(4, 3); else IMB_IL4(4, 2); }
-  else if (ng == 2) { if (minb >= 4) IMB_IL4(2, 4); else if (minb == 3) IMB_IL4(2, 3); else IMB_IL4(2, 2); }
+  if (ng == 4) { if (minb >= 3) IMB_IL4(4, 3); else if (minb == 1) IMB_IL4(4, 1); else IMB_IL4(4, 2); }
+  else if (ng == 2) { if (minb >= 4) IMB_IL4(2, 4); else if (minb == 3) IMB_IL4(2, 3); else if (minb == 1) IMB_IL4(2, 1); else IMB_IL4(2, 2); }
   else { if (minb >= 4) IMB_IL4(1, 4); else if (minb == 3) IMB_IL4(1, 3); else IMB_IL4(1, 2); }
 #undef IMB_IL4
 }
