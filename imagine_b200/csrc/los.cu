@@ -10,82 +10,12 @@
 // stage to hammurabiX, simulators/hammurabi.py:193-227).
 #include <cstdlib>
 #include "common.cuh"
+#include "los.cuh"
 
 namespace imb {
 
 int make_dev_grid(const imb_grid* grid, DevGrid* g);
-
-struct LosArgs {
-  DevGrid g;
-  double obs[3];
-  double dr, dl_pc, dl_cm, lam2;
-  int n_steps, m, n_real;
-  // constant-index synchrotron coefficients (beta == theta == 0)
-  double sync_k, pol_frac, expo;
-  // variable-index: K(p) = kA/(p+1) G(p/4+19/12) G(p/4-1/12) exp(kE0 + p*kE1)
-  double alpha, beta, theta, kA, kE0, kE1;
-  const double* dirs;
-  const double* B;   long long B_row;    // row stride in doubles (0 when rows == 1)
-  const double* ne;  long long ne_row;
-  const double* cre; long long cre_row;
-  double *out_dm, *out_fd, *out_I, *out_Q, *out_U;
-};
-
-__device__ __forceinline__ double4 ldg256(const double* p) {
-  double4 v;
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
-  return v;
-}
-
-__device__ __forceinline__ double lerp(double a, double b, double t) { return fma(t, b - a, a); }
-
-struct Cell {
-  long long base;       // linear index of the (ix,iy,iz) corner
-  long long sy, sx;     // strides to iy+1, ix+1 (in cells)
-  double tx, ty, tz;
-};
-
-__device__ __forceinline__ double interp_scalar(const double* __restrict__ f, const Cell& c) {
-  const double* p = f + c.base;
-  const double c00 = lerp(__ldg(p), __ldg(p + 1), c.tz);
-  const double c01 = lerp(__ldg(p + c.sy), __ldg(p + c.sy + 1), c.tz);
-  const double c10 = lerp(__ldg(p + c.sx), __ldg(p + c.sx + 1), c.tz);
-  const double c11 = lerp(__ldg(p + c.sx + c.sy), __ldg(p + c.sx + c.sy + 1), c.tz);
-  return lerp(lerp(c00, c01, c.ty), lerp(c10, c11, c.ty), c.tx);
-}
-
-template <int BS>
-__device__ __forceinline__ void zpair(const double* __restrict__ p, double tz, double& x,
-                                      double& y, double& z) {
-  if (BS == 4) {
-    const double4 a = ldg256(p), b = ldg256(p + 4);
-    x = lerp(a.x, b.x, tz); y = lerp(a.y, b.y, tz); z = lerp(a.z, b.z, tz);
-  } else {
-    const double a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
-    const double b0 = __ldg(p + 3), b1 = __ldg(p + 4), b2 = __ldg(p + 5);
-    x = lerp(a0, b0, tz); y = lerp(a1, b1, tz); z = lerp(a2, b2, tz);
-  }
-}
-
-template <int BS>
-__device__ __forceinline__ void interp_vector(const double* __restrict__ f, const Cell& c,
-                                              double& bx, double& by, double& bz) {
-  const double* p = f + c.base * BS;
-  double x00, y00, z00, x01, y01, z01, x10, y10, z10, x11, y11, z11;
-  zpair<BS>(p, c.tz, x00, y00, z00);
-  zpair<BS>(p + c.sy * BS, c.tz, x01, y01, z01);
-  zpair<BS>(p + c.sx * BS, c.tz, x10, y10, z10);
-  zpair<BS>(p + (c.sx + c.sy) * BS, c.tz, x11, y11, z11);
-  bx = lerp(lerp(x00, x01, c.ty), lerp(x10, x11, c.ty), c.tx);
-  by = lerp(lerp(y00, y01, c.ty), lerp(y10, y11, c.ty), c.tx);
-  bz = lerp(lerp(z00, z01, c.ty), lerp(z10, z11, c.ty), c.tx);
-}
-
-__device__ __forceinline__ double sync_coeff_var(const LosArgs& a, double p) {
-  return a.kA / (p + 1.0) * tgamma(p * 0.25 + 19.0 / 12.0) * tgamma(p * 0.25 - 1.0 / 12.0) *
-         exp(a.kE0 + p * a.kE1);
-}
+int launch_los_il4s(const LosArgs& a, bool has_ne, bool has_cre, bool var_p, cudaStream_t s);
 
 template <bool HAS_NE, bool HAS_CRE, bool VAR_P, int RT, int BS>
 __global__ void __launch_bounds__(256) los_kernel(const __grid_constant__ LosArgs a) {
@@ -517,7 +447,12 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
     rt = n_real >= 4 ? 4 : (n_real >= 2 ? 2 : 1);
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (b_stride == 16) {
+  if (b_stride == 16 && !getenv("IMB_LOS_REGISTER_ACC")) {
+    IMB_TRY(launch_los_il4s(a, has_ne, has_cre, var_p, s));
+    IMB_LAUNCHED();
+    return IMB_OK;
+  }
+  if (b_stride == 16) {      // first interleaved kernel (register accumulators), kept for A/B runs
     if (has_ne && has_cre) {
       if (var_p) launch_il4<true, true, true>(a, s);
       else launch_il4<true, true, false>(a, s);
