@@ -372,6 +372,15 @@ static void launch_rt(const LosArgs& a, int bs, int rt, cudaStream_t s) {
   else launch_bs<HAS_NE, HAS_CRE, VAR_P, 1>(a, bs, grid, s);
 }
 
+__global__ void pack_pairs_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                  long long n, double* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    reinterpret_cast<double2*>(out)[i] = make_double2(x[i], y[i]);
+}
+
+int grid_blocks(long long work, int threads, int per_sm);
+
 }  // namespace imb
 
 using namespace imb;
@@ -436,6 +445,15 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
   a.ne = ne;   a.ne_row = (ne && rows_ne > 1) ? a.g.ncell : 0;
   a.cre = cre; a.cre_row = (cre && rows_cre > 1) ? a.g.ncell : 0;
   a.out_dm = out_dm; a.out_fd = out_fd; a.out_I = out_I; a.out_Q = out_Q; a.out_U = out_U;
+  a.necre = nullptr;
+  if (b_stride == 16 && has_ne && has_cre && rows_ne == 1 && rows_cre == 1) {
+    // pack the two shared scalar grids into (n_e, CRE) pairs: one 128-bit gather per vertex
+    IMB_TRY(ensure_workspace(sizeof(double) * 2 * (size_t)a.g.ncell + 256));
+    double* packed = static_cast<double*>(state().ws);
+    pack_pairs_kernel<<<grid_blocks(a.g.ncell, 256, 8), 256, 0, (cudaStream_t)stream>>>(ne, cre, a.g.ncell, packed);
+    IMB_LAUNCHED();
+    a.necre = packed;
+  }
 
   // realisation tile: reuse geometry + deterministic interpolants across realisations
   int rt = 1;

@@ -17,6 +17,7 @@ struct LosArgs {
   const double* B;   long long B_row;    // row stride in doubles (0 when rows == 1)
   const double* ne;  long long ne_row;
   const double* cre; long long cre_row;
+  const double* necre;                   // packed (n_e, CRE) per vertex when both are shared, else NULL
   double *out_dm, *out_fd, *out_I, *out_Q, *out_U;
 };
 
@@ -42,6 +43,20 @@ __device__ __forceinline__ double interp_scalar(const double* __restrict__ f, co
   const double c10 = lerp(__ldg(p + c.sx), __ldg(p + c.sx + 1), c.tz);
   const double c11 = lerp(__ldg(p + c.sx + c.sy), __ldg(p + c.sx + c.sy + 1), c.tz);
   return lerp(lerp(c00, c01, c.ty), lerp(c10, c11, c.ty), c.tx);
+}
+
+// packed (n_e, CRE) pairs: one 128-bit load per vertex
+__device__ __forceinline__ void interp_pair(const double* __restrict__ f, const Cell& c, double& ne,
+                                            double& cre) {
+  const double2* p = reinterpret_cast<const double2*>(f) + c.base;
+  const double2 a0 = __ldg(p), a1 = __ldg(p + 1);
+  const double2 b0 = __ldg(p + c.sy), b1 = __ldg(p + c.sy + 1);
+  const double2 c0 = __ldg(p + c.sx), c1 = __ldg(p + c.sx + 1);
+  const double2 d0 = __ldg(p + c.sx + c.sy), d1 = __ldg(p + c.sx + c.sy + 1);
+  ne = lerp(lerp(lerp(a0.x, a1.x, c.tz), lerp(b0.x, b1.x, c.tz), c.ty),
+            lerp(lerp(c0.x, c1.x, c.tz), lerp(d0.x, d1.x, c.tz), c.ty), c.tx);
+  cre = lerp(lerp(lerp(a0.y, a1.y, c.tz), lerp(b0.y, b1.y, c.tz), c.ty),
+             lerp(lerp(c0.y, c1.y, c.tz), lerp(d0.y, d1.y, c.tz), c.ty), c.tx);
 }
 
 template <int BS>

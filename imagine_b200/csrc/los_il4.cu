@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256, MINB) los_il4s_kernel(const __grid_consta
   const long long sy = a.g.n[2], sx = (long long)a.g.n[1] * a.g.n[2];
   const long long group_stride = a.g.ncell * 16;
 
+  double dm_total = 0.0;                 // shared-n_e dispersion measure of this lane's samples
   for (int jb = pc.j_lo; jb <= j_hi; jb += 8) {
     const int j = jb + slot;
     // -- geometry: bit-identical to oracle/los.py:sample_geometry (no fma on this path)
@@ -104,9 +105,17 @@ __global__ void __launch_bounds__(256, MINB) los_il4s_kernel(const __grid_consta
 
     double ne_s = 0.0, cre_s = 0.0;
     const bool ne_shared = HAS_NE && a.ne_row == 0, cre_shared = HAS_CRE && a.cre_row == 0;
-    if (ne_shared) ne_s = inside ? interp_scalar(a.ne, c) : 0.0;
-    if (cre_shared) cre_s = inside ? interp_scalar(a.cre, c) : 0.0;
+    if (HAS_NE && HAS_CRE && a.necre) {
+      if (inside) interp_pair(a.necre, c, ne_s, cre_s);
+    } else {
+      if (ne_shared) ne_s = inside ? interp_scalar(a.ne, c) : 0.0;
+      if (cre_shared) cre_s = inside ? interp_scalar(a.cre, c) : 0.0;
+    }
+    // the dispersion measure does not depend on the realisation when n_e is shared
+    double dm_chunk = 0.0;
+    if (ne_shared) dm_chunk = ne_s * a.dl_pc;
 
+    dm_total += dm_chunk;
 #pragma unroll 1
     for (int t = 0; t < NG; ++t) {
       const int g = g0 + t;
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(256, MINB) los_il4s_kernel(const __grid_consta
         const double carry = acc[0];
         phi = (carry + x) - 0.5 * f;
         acc[0] = carry + __shfl_sync(0xffffffffu, x, 28 + r4);
-        acc[256] += ne_s * a.dl_pc;
+        if (!ne_shared) acc[256] += ne_s * a.dl_pc;
       }
       if (HAS_CRE) {
         if (!cre_shared) cre_s = live ? interp_scalar(a.cre + a.cre_row * rr, c) : 0.0;
@@ -180,12 +189,13 @@ __global__ void __launch_bounds__(256, MINB) los_il4s_kernel(const __grid_consta
     }
   }
 
+  const bool dm_shared = HAS_NE && a.ne_row == 0;
   for (int t = 0; t < NG; ++t) {
     const int g = g0 + t;
     if (g >= n_groups) break;
     const int rr = g * 4 + r4;
     const double* acc = s_acc + (size_t)(t * 5) * 256 + tid;
-    double dm = acc[256], I = acc[512], Q = acc[768], U = acc[1024];
+    double dm = dm_shared ? dm_total : acc[256], I = acc[512], Q = acc[768], U = acc[1024];
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) {
       if (HAS_NE) dm += __shfl_xor_sync(0xffffffffu, dm, o);
