@@ -1,0 +1,121 @@
+"""
+GPU, BASELINE.json full sizes: size-independent properties of the whole hot path where the NumPy
+oracle would take minutes.  C3 = 128^3 grid, Nside 64, 64 realisations; C2 = 64^3, Nside 32, 16.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import fields as OF          # noqa: E402
+from oracle import healpix as OH         # noqa: E402
+from oracle import likelihood as OK      # noqa: E402
+from oracle import los as OL             # noqa: E402
+
+BOX = [[-20.0, 20.0], [-20.0, 20.0], [-4.0, 4.0]]
+LOS_KW = dict(observer=(-8.3, 0.0, 0.006), dr=0.1, r_max=30.0, nu_ghz=23.0, alpha=3.0)
+DESCS = [(OF.EXP_NE, [0.01, 3.0, 0.1], 0), (OF.CONST_B, [0.0, 1.0, 0.0], 1), (OF.GAUSS_B, [0.0, 2.0], 2),
+         (OF.CRE_ANALYTIC, [0.0217, 5.0, 1.0, 8.3], 3)]
+
+
+@pytest.fixture(scope='module')
+def c3():
+    import torch
+    from imagine_b200 import engine, _lib
+    from imagine_b200.hotpath import EnsembleEvaluator
+    _lib.init(0)
+    np.random.seed(1)
+    seeds = np.random.randint(1, 1431655765, 64).astype(np.uint64)
+    ev = EnsembleEvaluator(BOX, [128] * 3, 64, engine.LosSettings(**LOS_KW), n_real=64)
+    maps = {k: v.clone() for k, v in ev.simulate(DESCS, seeds).items()}
+    torch.cuda.synchronize()
+    return engine, ev, seeds, maps
+
+
+def test_c3_shapes_finite_and_shared_dm(c3):
+    engine, ev, seeds, maps = c3
+    for q, t in maps.items():
+        assert tuple(t.shape) == (64, 49152) and bool(t.isfinite().all()), q
+    dm = maps['dm'].cpu().numpy()
+    assert np.array_equal(dm[0], dm[63])                 # deterministic n_e: DM independent of realisation
+    assert np.all(maps['I'].cpu().numpy() >= 0)
+    pi = np.sqrt(maps['Q'].cpu().numpy() ** 2 + maps['U'].cpu().numpy() ** 2)
+    assert np.all(pi <= 0.75 * maps['I'].cpu().numpy() * (1 + 1e-12))       # |P| <= Pi(p=3) * I
+
+
+def test_c3_pixel_subset_matches_oracle(c3):
+    """Oracle on 96 pixels spread over the sky x 2 realisations of the full 128^3 problem."""
+    engine, ev, seeds, maps = c3
+    from tests.helpers import b_to_reference_layout
+    pix = np.linspace(0, 49151, 96).astype(np.int64)
+    rows = [0, 37]
+    f = ev._field_bufs
+    og = OF.Grid(BOX, [128] * 3)
+    B = b_to_reference_layout(f['magnetic_field'], 64, og.shape)[rows]
+    ne = f['thermal_electron_density'].cpu().numpy().reshape(1, *og.shape)
+    cre = f['cosmic_ray_electron_density'].cpu().numpy().reshape(1, *og.shape)
+    want = OL.integrate(og, OL.LosConfig(**LOS_KW), OH.pix2vec_ring(64)[pix], B, ne, cre)
+    for q in ('dm', 'fd', 'I', 'Q', 'U'):
+        got = maps[q].cpu().numpy()[rows][:, pix]
+        scale = np.abs(want[q]).max()
+        assert np.abs(got - want[q]).max() <= 1e-9 * scale, q
+
+
+def test_c3_fields_deterministic_part_and_seed_reproducibility(c3):
+    engine, ev, seeds, maps = c3
+    og = OF.Grid(BOX, [128] * 3)
+    ne = ev._field_bufs['thermal_electron_density'].cpu().numpy().reshape(og.shape)
+    assert np.allclose(ne, OF.exponential_ne(og, 0.01, 3.0, 0.1), rtol=1e-9, atol=0)
+    # one realisation regenerated alone (different ensemble position, row-major layout) is bit-identical
+    from tests.helpers import b_to_reference_layout
+    one = engine.field_eval(ev.grid, DESCS[1:3], [seeds[5]], b_stride=4)['magnetic_field']
+    full = b_to_reference_layout(ev._field_bufs['magnetic_field'], 64, og.shape)[5]
+    assert np.array_equal(b_to_reference_layout(one, 1, og.shape)[0], full)
+
+
+def test_c3_likelihood_gram_vs_numpy_gram_and_sharding_invariance(c3):
+    engine, ev, seeds, maps = c3
+    import torch
+    total_gpu, total_np = 0.0, 0.0
+    meas, var = {}, {}
+    for q, t in maps.items():
+        sigma = 0.01 * float(t[0].abs().mean())
+        meas[q] = (t[0] * 1.003 + sigma).contiguous()
+        var[q] = torch.full((49152,), sigma ** 2, dtype=torch.float64, device='cuda')
+    got = ev.loglike(maps, meas, var)
+    for q, t in maps.items():
+        total_np += OK.ensemble_loglike_gram(t.cpu().numpy(), meas[q].cpu().numpy(), var[q].cpu().numpy())
+    assert abs(got - total_np) <= 1e-8 * max(1.0, abs(total_np) * 1e-6), (got, total_np)
+    # simulating the ensemble in two halves (what 2 ranks do) gives bit-identical maps
+    from imagine_b200.hotpath import EnsembleEvaluator
+    for rank in (0, 1):
+        half = EnsembleEvaluator(BOX, [128] * 3, 64, ev.settings, n_real=64, rank=rank, world=2)
+        local = half.simulate(DESCS, seeds)
+        for q in maps:
+            assert torch.equal(local[q], maps[q][rank * 32:(rank + 1) * 32]), (rank, q)
+        del half
+
+
+def test_c2_dense_route_equals_gram_route_at_nside32():
+    """configs[1]: Nside 32 (m = 12 288), 64^3 grid, 16 realisations: DMMA SYRK + blocked Cholesky."""
+    import time
+    import torch
+    from imagine_b200 import engine, _lib
+    from imagine_b200.hotpath import EnsembleEvaluator
+    _lib.init(0)
+    np.random.seed(1)
+    seeds = np.random.randint(1, 1431655765, 16).astype(np.uint64)
+    ev = EnsembleEvaluator(BOX, [64] * 3, 32, engine.LosSettings(**LOS_KW), quantities=('fd',), n_real=16)
+    fd = ev.simulate(DESCS[:3], seeds)['fd']
+    sigma = 0.01 * float(fd.abs().mean())
+    meas = (fd[3] + sigma).contiguous()
+    var = torch.full((12288,), sigma ** 2, dtype=torch.float64, device='cuda')
+    g = engine.loglike_ensemble(fd, meas, var, route='gram')
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d, info = engine.loglike_ensemble(fd, meas, var, route='dense', return_info=True)
+    dt = time.perf_counter() - t0
+    assert info[0] & 4                                    # Cholesky
+    # same number from the m x m factorisation and from the N x N Gram matrix (SURVEY finding 5)
+    assert abs(d - g) <= 1e-8 * max(1.0, abs(g) * 1e-5), (d, g, dt)
+    print('dense route m=12288: %.3f s' % dt)
