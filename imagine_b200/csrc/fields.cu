@@ -95,16 +95,13 @@ __global__ void __launch_bounds__(256) field_b_kernel(const __grid_constant__ Fi
 // cells, realisation), r4 fastest, so a warp writes 2 KB contiguous.
 __global__ void __launch_bounds__(256) field_b_il4_kernel(const __grid_constant__ FieldArgs a,
                                                           double* __restrict__ out) {
-  const long long npair = (a.g.ncell + 1) >> 1;
-  const long long n_groups = (a.rows + 3) >> 2;
-  const long long total = npair * n_groups * 4;
-  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
-       w += (long long)gridDim.x * blockDim.x) {
-    const int r4 = (int)(w & 3);
-    const long long t_ = w >> 2;
-    const long long g = t_ / npair;
-    const long long q = t_ - g * npair;
-    const int r = (int)(g * 4 + r4);
+  // grid = (pair blocks, realisation groups): all index arithmetic stays 32-bit (no 64-bit division)
+  const unsigned int npair4 = (unsigned int)((a.g.ncell + 1) >> 1) * 4u;
+  const int g = blockIdx.y;
+  for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < npair4; w += gridDim.x * blockDim.x) {
+    const int r4 = (int)(w & 3u);
+    const unsigned int q = w >> 2;
+    const int r = g * 4 + r4;
     double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (r < a.rows) {
       bool first = true;
@@ -119,7 +116,7 @@ __global__ void __launch_bounds__(256) field_b_il4_kernel(const __grid_constant_
 #pragma unroll
           for (int b = 0; b < 3; ++b) {
             double z0, z1;
-            philox_normal_pair(seed, a.stream[f], (unsigned long long)(3 * q + b), z0, z1);
+            philox_normal_pair(seed, a.stream[f], 3ull * q + b, z0, z1);
             t[2 * b] = __dadd_rn(__dmul_rn(z0, sigma), mu);
             t[2 * b + 1] = __dadd_rn(__dmul_rn(z1, sigma), mu);
           }
@@ -129,8 +126,8 @@ __global__ void __launch_bounds__(256) field_b_il4_kernel(const __grid_constant_
         first = false;
       }
     }
-    const long long c0 = 2 * q;
-    double* o = out + ((g * a.g.ncell + c0) * 4 + r4) * 4;
+    const long long c0 = 2ll * q;
+    double* o = out + (((long long)g * a.g.ncell + c0) * 4 + r4) * 4;
     *reinterpret_cast<double4*>(o) = make_double4(v[0], v[1], v[2], 0.0);
     if (c0 + 1 < a.g.ncell) *reinterpret_cast<double4*>(o + 16) = make_double4(v[3], v[4], v[5], 0.0);
   }
@@ -420,8 +417,12 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
       if (b_stride == 16) {
         // realisation-interleaved: [ceil(rows/4), ncell, 4, 4]; only meaningful per realisation
         if (need != n_real || addr % 32 != 0) return IMB_EINVAL;
-        const long long work4 = ((g.ncell + 1) / 2) * ((need + 3) / 4) * 4;
-        field_b_il4_kernel<<<grid_blocks(work4, 256, 8), 256, 0, stream>>>(a, outs[type]);
+        if (g.ncell >= (1ll << 30)) return IMB_EUNSUPPORTED;   // 32-bit pair index
+        const int n_groups = (need + 3) / 4;
+        const long long work4 = ((g.ncell + 1) / 2) * 4;
+        int bx = grid_blocks(work4, 256, 8) / n_groups;
+        if (bx < 1) bx = 1;
+        field_b_il4_kernel<<<dim3(bx, n_groups), 256, 0, stream>>>(a, outs[type]);
       } else if (b_stride == 3) {
         const bool vec = (addr % 16 == 0) && (need == 1 || row_elems % 2 == 0);
         if (vec) field_b_kernel<3, true><<<blocks, 256, 0, stream>>>(a, outs[type]);

@@ -18,7 +18,7 @@
 namespace imb {
 
 constexpr int KMAX = 16;           // observables per batch launch
-constexpr int GCOLS = 256;         // columns per Gram slice (fixed => summation order depends on m only)
+constexpr int GCOLS = 768;        // columns per Gram slice (fixed => summation order depends on m only)
 
 struct BatchPtrs {
   const double* sims[KMAX];
@@ -226,11 +226,12 @@ __global__ void __launch_bounds__(256) bg_finish_kernel(const __grid_constant__ 
     const double pv = T[(size_t)k * ldt + k];
     if (tid == 0 && !(pv > 0.0) && bad == 0) bad = k + 1;
     const double inv = 1.0 / pv;
-    const int rem = N - k;                       // rows k+1 .. N, columns k+1 .. N-1
-    for (int e = tid; e < rem * (rem - 1); e += nt) {
-      const int i = k + 1 + e / (rem - 1), j = k + 1 + e % (rem - 1);
-      if (j <= i && j < N)
-        T[(size_t)i * ldt + j] -= T[(size_t)i * ldt + k] * T[(size_t)j * ldt + k] * inv;
+    // rows k+1 .. N (row N = rhs), columns k+1 .. min(i, N-1): warp per row, lanes along columns
+    for (int i = k + 1 + (tid >> 5); i <= N; i += (nt >> 5)) {
+      const double lik = T[(size_t)i * ldt + k] * inv;
+      const int jmax = i < N ? i : N - 1;
+      for (int j = k + 1 + (tid & 31); j <= jmax; j += 32)
+        T[(size_t)i * ldt + j] -= lik * T[(size_t)j * ldt + k];
     }
     if (tid == 0) {
       ld += log(pv);                             // log|K| = sum log(pivot)
