@@ -76,7 +76,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -171,7 +171,7 @@ def workload_config(name, w, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
@@ -346,8 +346,13 @@ def main():
                     'ms_per_step': max(e2e_ms, e2e_wall_ms) / args.steps},
             'gpu_launches': int(launches),
             'clocks': clocks,
-            'roofline': {'kernel': 'los_kernel', 'bound': 'hbm', 'achieved': los_gbs, 'peak': peak,
-                         'unit': 'GB/s', 'frac': los_gbs / peak, 'traffic': None,
+            'roofline': {'kernel': 'los_il4s_kernel', 'bound': 'hbm', 'achieved': los_gbs, 'peak': peak,
+                         'unit': 'GB/s', 'frac': los_gbs / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full,
+                         # profiles/r01_ncu_full_v3_los_il4s.csv (c3, 1 GPU only)
+                         'traffic': 3919345136 if (args.workload == 'c3' and world == 1) else None,
+                         'limiter': 'L1 data-pipe wavefronts of the trilinear gathers (86 % of peak); '
+                                    'the padded B grid leaves HBM once (DRAM 8 % busy)',
                          'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)',
                          'algorithmic_bytes_per_launch': int(los_bytes),
                          'ms_per_launch': stage[1]},

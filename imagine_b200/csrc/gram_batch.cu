@@ -18,7 +18,7 @@
 namespace imb {
 
 constexpr int KMAX = 16;           // observables per batch launch
-constexpr int GCOLS = 768;        // columns per Gram slice (fixed => summation order depends on m only)
+constexpr int GCOLS = 256;         // columns per Gram slice (fixed => summation order depends on m only)
 
 struct BatchPtrs {
   const double* sims[KMAX];
