@@ -176,6 +176,7 @@ def main():
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'alltoall', 'allgather'])
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -205,10 +206,11 @@ def main():
     descs = field_descs(quantities)
     seeds = ensemble_seeds(N)
     settings = engine.LosSettings(**LOS_KW)
-    ev = EnsembleEvaluator(BOX, [G] * 3, nside, settings, quantities, n_real=N, rank=rank, world=world)
+    ev = EnsembleEvaluator(BOX, [G] * 3, nside, settings, quantities, n_real=N, rank=rank, world=world,
+                           exchange=args.exchange)
 
     # ---- synthetic measurements: one realisation from an independent seed + 1% noise --------
-    mock = EnsembleEvaluator(BOX, [G] * 3, nside, settings, quantities, n_real=1)
+    mock = EnsembleEvaluator(BOX, [G] * 3, nside, settings, quantities, n_real=1, exchange='allgather')
     mock.simulate(descs, np.array([987654321], dtype=np.uint64))
     gen = torch.Generator(device='cuda').manual_seed(2026)
     meas_h, var_h = {}, {}

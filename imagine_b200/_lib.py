@@ -43,9 +43,9 @@ class FieldDesc(C.Structure):
 
 class LosCfg(C.Structure):
     _fields_ = [('observer', C.c_double * 3), ('dr', C.c_double), ('n_steps', C.c_int32),
-                ('reserved', C.c_int32), ('nu_ghz', C.c_double), ('alpha', C.c_double),
+                ('out_cols_per_dest', C.c_int32), ('nu_ghz', C.c_double), ('alpha', C.c_double),
                 ('beta', C.c_double), ('theta', C.c_double), ('e0_gev', C.c_double),
-                ('sync_k', C.c_double)]
+                ('sync_k', C.c_double), ('out_dest_stride', C.c_int64)]
 
 
 _P = C.c_void_p
@@ -73,6 +73,11 @@ _SIGNATURES = {
                                        C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int32), _P]),
     'imb_loglike_ensemble_batch': (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_int,
                                              C.POINTER(C.c_double), C.POINTER(C.c_int32), _P]),
+    'imb_gram_phase1': (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, _P]),
+    'imb_gram_phase2': (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P,
+                                  C.c_int64, C.c_int, _P, _P, _P]),
+    'imb_gram_phase3': (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_double),
+                                  C.POINTER(C.c_int32), _P]),
     'imb_loglike_ensemble_diagonal': (C.c_int, [_P, C.c_int, C.c_int, _P, _P,
                                                 C.POINTER(C.c_double), _P]),
     'imb_loglike_simple': (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int,

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) los_kernel(const __grid_constant__ LosArg
   for (int t = 0; t < RT; ++t) {
     const int rr = r0 + t;
     if (rr >= a.n_real) break;
-    const long long o = (long long)rr * a.m + pix;
+    const long long o = out_index(a, rr, pix);
     if (HAS_NE) {
       const double dm = warp_sum(accDM[t]);
       if (lane == 0) {
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256, MINB) los_il4_kernel(const __grid_constan
       }
     }
     if (slot == 0 && rr < a.n_real) {
-      const long long o = (long long)rr * a.m + pix;
+      const long long o = out_index(a, rr, pix);
       if (HAS_NE) {
         if (a.out_dm) a.out_dm[o] = dm;
         if (a.out_fd) a.out_fd[o] = carry[t];
@@ -446,6 +446,12 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
   a.cre = cre; a.cre_row = (cre && rows_cre > 1) ? a.g.ncell : 0;
   a.out_dm = out_dm; a.out_fd = out_fd; a.out_I = out_I; a.out_Q = out_Q; a.out_U = out_U;
   a.necre = nullptr;
+  a.out_mp = m; a.out_dest = 0;
+  if (cfg->out_cols_per_dest > 0) {
+    if (m % cfg->out_cols_per_dest != 0 || cfg->out_dest_stride < 0) return IMB_EINVAL;
+    a.out_mp = cfg->out_cols_per_dest;
+    a.out_dest = cfg->out_dest_stride;
+  }
   if (b_stride == 16 && has_ne && has_cre && rows_ne == 1 && rows_cre == 1) {
     // pack the two shared scalar grids into (n_e, CRE) pairs: one 128-bit gather per vertex
     IMB_TRY(ensure_workspace(sizeof(double) * 2 * (size_t)a.g.ncell + 256));
@@ -458,6 +464,7 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
   // realisation tile: reuse geometry + deterministic interpolants across realisations
   int rt = 1;
   const bool per_real = rows_B > 1 || rows_ne > 1 || rows_cre > 1;
+  if (!per_real && cfg->out_cols_per_dest > 0) return IMB_EUNSUPPORTED;
   if (!per_real) {
     // every realisation is identical: compute one row, replicate below
     a.n_real = 1;

@@ -19,7 +19,16 @@ struct LosArgs {
   const double* cre; long long cre_row;
   const double* necre;                   // packed (n_e, CRE) per vertex when both are shared, else NULL
   double *out_dm, *out_fd, *out_I, *out_Q, *out_U;
+  // output addressing: row-major [n_real, m] (out_mp == m, out_dest == 0) or, for a pixel-sharded
+  // exchange, [dest][...][n_real][out_mp] with `out_dest` doubles between destination blocks
+  int out_mp;
+  long long out_dest;
 };
+
+__device__ __forceinline__ long long out_index(const LosArgs& a, int rr, int pix) {
+  const int dest = pix / a.out_mp;
+  return (long long)dest * a.out_dest + (long long)rr * a.out_mp + (pix - dest * a.out_mp);
+}
 
 __device__ __forceinline__ double4 ldg256(const double* p) {
   double4 v;

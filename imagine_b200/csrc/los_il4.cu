@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256, MINB) los_il4s_kernel(const __grid_consta
       }
     }
     if (slot == 0 && rr < a.n_real) {
-      const long long o = (long long)rr * a.m + pix;
+      const long long o = out_index(a, rr, pix);
       if (HAS_NE) {
         if (a.out_dm) a.out_dm[o] = dm;
         if (a.out_fd) a.out_fd[o] = acc[0];

@@ -55,8 +55,9 @@ class LosSettings:
         return LosSettings(self.observer, self.dr, None, self.n_steps, nu_ghz, self.alpha,
                            self.beta, self.theta, self.e0_gev)
 
-    def c_struct(self):
+    def c_struct(self, out_cols_per_dest=0, out_dest_stride=0):
         cfg = L.LosCfg()
+        cfg.out_cols_per_dest, cfg.out_dest_stride = int(out_cols_per_dest), int(out_dest_stride)
         for a in range(3):
             cfg.observer[a] = self.observer[a]
         cfg.dr, cfg.n_steps, cfg.nu_ghz = self.dr, self.n_steps, self.nu_ghz
@@ -156,10 +157,12 @@ def healpix_ring_dirs(nside):
 
 
 def los_integrate(grid, settings, dirs, B, ne=None, cre=None, n_real=1,
-                  want=('dm', 'fd', 'I', 'Q', 'U'), out=None):
+                  want=('dm', 'fd', 'I', 'Q', 'U'), out=None, out_layout=None):
     """
     Integrate every realisation along `dirs` [m,3] (imb_los_integrate).  Returns a dict of
-    [n_real, m] tensors for the requested quantities.
+    [n_real, m] tensors for the requested quantities.  With `out_layout = (cols_per_dest,
+    dest_stride)` the tensors in `out` are base pointers of a pixel-sharded send buffer
+    (pixel p of realisation r at (p // cols) * dest_stride + r * cols + p % cols).
     """
     torch = _torch()
     L.init()
@@ -175,7 +178,7 @@ def los_integrate(grid, settings, dirs, B, ne=None, cre=None, n_real=1,
                 res[k] = out[k]
             else:
                 res[k] = torch.empty((n_real, m), dtype=torch.float64, device=B.device)
-    cfg = settings.c_struct()
+    cfg = settings.c_struct(*(out_layout or (0, 0)))
     interleaved = B.dim() == 4                      # [group][cell][4][4] realisation-interleaved layout
     L.check(L.load().imb_los_integrate(
         C.byref(grid.c), C.byref(cfg), L.ptr(dirs), m, L.ptr(B),
@@ -281,6 +284,40 @@ def loglike_ensemble_batch(sims, meas, var, estimator='oas', return_info=False):
                                                 out, info, L.stream_ptr()))
     vals = [out[k] for k in range(K)]
     return (vals, [(info[2 * k], info[2 * k + 1]) for k in range(K)]) if return_info else vals
+
+
+def _ptr_array(ts):
+    return (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+
+def gram_phase1(sims, N, m_local, layout, meas, G):
+    """imb_gram_phase1: partial Gram of the local pixels of every key into G [K, N, N]."""
+    L.init()
+    rpb, bstride, rstride = layout
+    L.check(L.load().imb_gram_phase1(len(sims), _ptr_array(sims), N, m_local, rpb, bstride, rstride,
+                                     _ptr_array(meas), L.ptr(G), L.stream_ptr()))
+
+
+def gram_phase2(sims, N, m_local, layout, meas, var, m_total, G, P2, estimator='oas'):
+    """imb_gram_phase2: shrinkage from the (all-reduced) G, then the partial P2 [K, N*N+N+4]."""
+    L.init()
+    rpb, bstride, rstride = layout
+    L.check(L.load().imb_gram_phase2(len(sims), _ptr_array(sims), N, m_local, rpb, bstride, rstride,
+                                     _ptr_array(meas), _ptr_array(var), int(m_total), _EST[estimator],
+                                     L.ptr(G), L.ptr(P2), L.stream_ptr()))
+
+
+def gram_phase3(K, N, m_local, G, P2):
+    """imb_gram_phase3: per-key log-likelihoods from the (all-reduced) P2; list of floats."""
+    L.init()
+    out, info = (C.c_double * K)(), (C.c_int32 * (2 * K))()
+    L.check(L.load().imb_gram_phase3(K, N, m_local, L.ptr(G), L.ptr(P2), out, info, L.stream_ptr()))
+    for k in range(K):
+        if info[2 * k + 1] != 0:
+            raise np.linalg.LinAlgError('Gram route not applicable for key %d (info %d): non-positive '
+                                        'shrunk diagonal; gather the maps and use the dense route'
+                                        % (k, info[2 * k + 1]))
+    return [out[k] for k in range(K)]
 
 
 def loglike_ensemble_diagonal(sims, meas, var):

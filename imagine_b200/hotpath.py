@@ -4,17 +4,28 @@ One ensemble log-likelihood evaluation on device: fields -> LOS maps -> log-like
 `EnsembleEvaluator` owns the device buffers of one parameter-point evaluation and shards the
 ensemble over ranks the way the reference's `distribute_ensemble` does
 (pipelines/pipeline.py:737-744: contiguous blocks of N/P realisations, N a multiple of P).
-Randomness is keyed on the GLOBAL realisation seed, so results do not depend on P.  The only
-exchange is one NCCL all-gather of the simulated maps per observable; every rank then forms
-the N x N Gram matrix redundantly and returns the identical scalar ("copied to all nodes",
-likelihoods/ensemble_likelihood.py:79-80).  The GPU Simulator / Likelihood drop-ins
-(api/gpu_simulator.py, api/gpu_likelihood.py) are thin shells over this class.
+Randomness is keyed on the GLOBAL realisation seed, so results do not depend on P.
+
+Two exchange modes between the simulation and the likelihood:
+
+  'alltoall'  (default when P divides the pixel count)  The LOS kernel writes its maps directly in
+              destination-major order [P][K][n_local][m/P]; ONE all-to-all then gives every rank
+              all N realisations of its m/P pixels of every observable (1/P of the all-gather
+              volume).  The Gram route runs in three phases on the local pixels with two small
+              SUM all-reduces in between (G: K*N*N doubles, P2: K*(N*N+N+4) doubles) -- the
+              exchange the reference does with mpi4py Allreduce / ring matmul
+              (tools/mpi_helper.py:132, 234-246).  The likelihood work is sharded P ways.
+  'allgather' Every rank receives every realisation's full maps (one all-gather per observable)
+              and evaluates the likelihood redundantly; what the plugin API needs, since
+              `Simulations` must expose the full [N, m] block.
+
+Either way every rank returns the identical scalar ("copied to all nodes",
+likelihoods/ensemble_likelihood.py:79-80).
 """
 import numpy as np
 
 from . import engine
 
-# observable name -> (LOS output, needs)
 LOS_OUTPUT = {'fd': 'fd', 'dm': 'dm', 'I': 'I', 'Q': 'Q', 'U': 'U'}
 
 
@@ -23,6 +34,14 @@ def shard_bounds(n_real, rank, world):
     if n_real % world != 0:
         raise ValueError('ensemble size %d is not a multiple of the number of ranks %d' % (n_real, world))
     per = n_real // world
+    return rank * per, (rank + 1) * per
+
+
+def pixel_bounds(m, rank, world):
+    """Contiguous pixel block of `rank` in the pixel-sharded likelihood (needs P | m)."""
+    if m % world != 0:
+        raise ValueError('pixel count %d is not a multiple of the number of ranks %d' % (m, world))
+    per = m // world
     return rank * per, (rank + 1) * per
 
 
@@ -41,9 +60,24 @@ def gather_rows(local, n_real, group=None):
     return full
 
 
+def exchange_pixel_shards(send, group=None):
+    """
+    All-to-all of a destination-major buffer [P, K, n_local, m/P]: block p goes to rank p; the
+    result [P, K, n_local, m/P] holds, for source rank q, its n_local realisations of MY pixels.
+    Backend-agnostic (NCCL / gloo).  Single rank: identity.
+    """
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return send
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    return recv
+
+
 class EnsembleEvaluator:
     def __init__(self, box, resolution, nside, los_settings, quantities=('fd', 'dm', 'I', 'Q', 'U'),
-                 n_real=1, rank=0, world=1, b_stride=16, group=None):
+                 n_real=1, rank=0, world=1, b_stride=16, group=None, exchange='auto'):
         import torch
         self.torch = torch
         self.grid = engine.DeviceGrid(box, resolution)
@@ -51,6 +85,7 @@ class EnsembleEvaluator:
         self.m = 12 * self.nside ** 2
         self.settings = los_settings
         self.quantities = tuple(quantities)
+        self.K = len(self.quantities)
         self.n_real = int(n_real)
         self.rank, self.world, self.group = int(rank), int(world), group
         self.lo, self.hi = shard_bounds(self.n_real, self.rank, self.world)
@@ -59,13 +94,27 @@ class EnsembleEvaluator:
         self.dirs = engine.healpix_ring_dirs(self.nside)
         self._field_bufs = {}
         dev = self.dirs.device
-        self.local_maps = {q: torch.empty((self.n_local, self.m), dtype=torch.float64, device=dev)
-                           for q in self.quantities}
-        if self.world > 1:
-            self.full_maps = {q: torch.empty((self.n_real, self.m), dtype=torch.float64, device=dev)
-                              for q in self.quantities}
+        if exchange == 'auto':
+            exchange = 'alltoall' if (self.world > 1 and self.m % self.world == 0) else 'allgather'
+        self.exchange = exchange
+        f64 = torch.float64
+        if self.exchange == 'alltoall':
+            self.mp = self.m // self.world
+            self.plo, self.phi = pixel_bounds(self.m, self.rank, self.world)
+            # destination-major send buffer the LOS kernel writes into; recv after the all-to-all
+            self.send = torch.empty((self.world, self.K, self.n_local, self.mp), dtype=f64, device=dev)
+            self.recv = self.send if self.world == 1 else torch.empty_like(self.send)
+            self.G = torch.empty((self.K, self.n_real, self.n_real), dtype=f64, device=dev)
+            self.P2 = torch.empty((self.K, self.n_real * self.n_real + self.n_real + 4), dtype=f64, device=dev)
+            self.local_maps = None
         else:
-            self.full_maps = self.local_maps
+            self.local_maps = {q: torch.empty((self.n_local, self.m), dtype=f64, device=dev)
+                               for q in self.quantities}
+            if self.world > 1:
+                self.full_maps = {q: torch.empty((self.n_real, self.m), dtype=f64, device=dev)
+                                  for q in self.quantities}
+            else:
+                self.full_maps = self.local_maps
 
     # -- stage 1 + 2 -----------------------------------------------------------------------
     def fields(self, descs, seeds):
@@ -86,19 +135,30 @@ class EnsembleEvaluator:
 
     def los(self, fields):
         want = tuple(LOS_OUTPUT[q] for q in self.quantities)
+        if self.exchange == 'alltoall':
+            out = {LOS_OUTPUT[q]: self.send[0, k] for k, q in enumerate(self.quantities)}
+            layout = (self.mp, self.K * self.n_local * self.mp)
+        else:
+            out = {LOS_OUTPUT[q]: self.local_maps[q] for q in self.quantities}
+            layout = None
         return engine.los_integrate(self.grid, self.settings, self.dirs, fields['magnetic_field'],
                                     fields.get('thermal_electron_density'),
                                     fields.get('cosmic_ray_electron_density'), n_real=self.n_local,
-                                    want=want, out={LOS_OUTPUT[q]: self.local_maps[q] for q in self.quantities})
+                                    want=want, out=out, out_layout=layout)
 
     def simulate(self, descs, seeds):
-        """Local maps {quantity: [n_local, m]} for this rank's block of realisations."""
+        """Run fields + LOS for this rank's block of realisations (outputs stay in device buffers)."""
         self.los(self.fields(descs, seeds))
-        return self.local_maps
+        return self.local_maps if self.exchange == 'allgather' else self.send
 
     # -- exchange ----------------------------------------------------------------------------
     def gather(self):
-        """All ranks end with every realisation's maps, rows in global order."""
+        """Move the simulated maps to where the likelihood needs them."""
+        if self.exchange == 'alltoall':
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_to_all_single(self.recv, self.send, group=self.group)
+            return self.recv
         if self.world == 1:
             return self.local_maps
         import torch.distributed as dist
@@ -106,16 +166,38 @@ class EnsembleEvaluator:
             dist.all_gather_into_tensor(self.full_maps[q], self.local_maps[q], group=self.group)
         return self.full_maps
 
+    def full_maps_from_shards(self, recv=None):
+        """[K][N, m_local] views of the received pixel shards in global realisation order (tests)."""
+        recv = self.recv if recv is None else recv
+        return {q: recv[:, k].reshape(self.n_real, self.mp) for k, q in enumerate(self.quantities)}
+
     # -- stage 3 -------------------------------------------------------------------------------
     def loglike(self, maps, meas, var, estimator='oas'):
         """Sum over observables of EnsembleLikelihood's per-key term (diagonal measurement cov)."""
         qs = self.quantities
-        vals = engine.loglike_ensemble_batch([maps[q] for q in qs], [meas[q] for q in qs],
-                                             [var[q] for q in qs], estimator=estimator)
+        if self.exchange == 'alltoall':
+            sims = [maps[0, k] for k in range(self.K)]        # base pointer of key k, blocked rows
+            layout = (self.n_local, self.K * self.n_local * self.mp, self.mp)
+            meas_l = [meas[q][self.plo:self.phi] for q in qs]
+            var_l = [var[q][self.plo:self.phi] for q in qs]
+            engine.gram_phase1(sims, self.n_real, self.mp, layout, meas_l, self.G)
+            self._allreduce(self.G)
+            engine.gram_phase2(sims, self.n_real, self.mp, layout, meas_l, var_l, self.m, self.G, self.P2,
+                               estimator=estimator)
+            self._allreduce(self.P2)
+            vals = engine.gram_phase3(self.K, self.n_real, self.mp, self.G, self.P2)
+        else:
+            vals = engine.loglike_ensemble_batch([maps[q] for q in qs], [meas[q] for q in qs],
+                                                 [var[q] for q in qs], estimator=estimator)
         total = 0.0
         for v in vals:                      # same left-to-right sum as the reference's loop over keys
             total += v
         return total
+
+    def _allreduce(self, t):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
     def evaluate(self, descs, seeds, meas, var, estimator='oas'):
         self.simulate(descs, seeds)

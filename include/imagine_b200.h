@@ -75,11 +75,14 @@ typedef struct {
   double observer[3];  /* Galactic-centric observer position [kpc] (test_ham.xml:26-30)   */
   double dr;           /* radial step oc_r_res [kpc]                                      */
   int32_t n_steps;     /* samples at r_j = (j+1/2) dr, j = 0..n_steps-1                   */
-  int32_t reserved;
+  int32_t out_cols_per_dest; /* 0: outputs are row-major [n_real, m].  > 0 (must divide m): pixel-  */
+                       /* sharded layout, pixel p of realisation r at                      */
+                       /* (p / cols) * out_dest_stride + r * cols + p % cols               */
   double nu_ghz;       /* synchrotron frequency [GHz]                                     */
   double alpha, beta, theta; /* CRE spectral index p = alpha - beta*R - theta*z           */
   double e0_gev;       /* CRE reference energy [GeV]                                      */
   double sync_k;       /* K(alpha,nu) computed by the host when beta == theta == 0        */
+  int64_t out_dest_stride;   /* doubles between destination blocks (see out_cols_per_dest)  */
 } imb_los_cfg;
 
 /* ---- likelihood options ------------------------------------------------------------ */
@@ -207,6 +210,30 @@ int imb_loglike_ensemble_batch(int K, const double* const* sims, int N, int m,
                                const double* const* meas, const double* const* var,
                                int estimator, double* out_loglike, int32_t* out_info,
                                void* stream);
+
+/*
+ * The same Gram route in three phases for an ensemble whose PIXELS are sharded over ranks (each
+ * rank holds all N realisations of m_local of the m_total pixels of every key, e.g. after an
+ * all-to-all of the per-rank map blocks).  Row r of key k lives at
+ *   sims[k] + (r / rows_per_block) * block_stride + (r % rows_per_block) * row_stride.
+ *   phase 1: G[K,N,N] (device, caller-owned) <- partial Gram of the local pixels.  SUM-all-reduce G.
+ *   phase 2: P2[K, N*N+N+4] <- partial weighted Gram, y, diagonal sums (needs the reduced G and
+ *            m_total).  SUM-all-reduce P2.
+ *   phase 3: K = I + c Gw, Cholesky, log-likelihood per key -> out_loglike HOST [K]; every rank
+ *            gets the identical number.  out_info[2k+1] = -1 flags a non-positive shrunk diagonal
+ *            (fall back to imb_loglike_ensemble on gathered maps).  Synchronises.
+ * The three calls of one evaluation must not be interleaved with other library calls (they share
+ * the scratch workspace).  K <= 16.  meas/var point at the LOCAL pixel slices.
+ */
+int imb_gram_phase1(int K, const double* const* sims, int N, int m_local, int rows_per_block,
+                    int64_t block_stride, int64_t row_stride, const double* const* meas, double* G,
+                    void* stream);
+int imb_gram_phase2(int K, const double* const* sims, int N, int m_local, int rows_per_block,
+                    int64_t block_stride, int64_t row_stride, const double* const* meas,
+                    const double* const* var, int64_t m_total, int estimator, double* G, double* P2,
+                    void* stream);
+int imb_gram_phase3(int K, int N, int m_local, double* G, double* P2, double* out_loglike,
+                    int32_t* out_info, void* stream);
 
 /* EnsembleLikelihoodDiagonal.call (likelihoods/ensemble_likelihood.py:137-173);
  * var [m] = diagonal of the measurement covariance.  Synchronises. */

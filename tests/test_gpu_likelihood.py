@@ -224,3 +224,46 @@ def test_batched_route_falls_back_per_key_on_nonpositive_variance(eng):
     for k in range(2):
         want = OK.ensemble_loglike(sims[k], meas[k], var[k])
         assert abs(got[k] - want) <= 1e-8 * max(1.0, abs(want))
+
+
+@pytest.mark.parametrize('N,m,K,P', [(8, 96, 2, 4), (64, 3072, 3, 8), (12, 1000, 1, 5)])
+def test_phased_gram_route_over_pixel_shards(eng, N, m, K, P):
+    """
+    imb_gram_phase1/2/3 on P pixel slices (what P ranks hold after the all-to-all, blocked row
+    layout [src][K][n_local][m/P]) with the two SUM reductions done by hand == the batch result.
+    """
+    import torch
+    rng = np.random.default_rng(N * m + P)
+    n_local, mp = N // (P if N % P == 0 else 1), m // P
+    S = P if N % P == 0 else 1                      # number of source blocks of rows
+    sims = [rng.normal(size=(N, m)) * (k + 1) + rng.normal(size=m) for k in range(K)]
+    meas = [rng.normal(size=m) for _ in range(K)]
+    var = [rng.uniform(0.3, 1.2, size=m) for _ in range(K)]
+    for est in ('oas', 'empirical'):
+        want = eng.loglike_ensemble_batch([_dev(s) for s in sims], [_dev(y) for y in meas],
+                                          [_dev(v) for v in var], estimator=est)
+        shards = []
+        for p in range(P):                          # what rank p receives: [S, K, n_local, mp]
+            buf = np.empty((S, K, n_local, mp))
+            for k in range(K):
+                buf[:, k] = sims[k][:, p * mp:(p + 1) * mp].reshape(S, n_local, mp)
+            shards.append(_dev(buf))
+        layout = (n_local, K * n_local * mp, mp)
+        meas_l = [[_dev(meas[k][p * mp:(p + 1) * mp]) for k in range(K)] for p in range(P)]
+        var_l = [[_dev(var[k][p * mp:(p + 1) * mp]) for k in range(K)] for p in range(P)]
+        G = torch.zeros((K, N, N), dtype=torch.float64, device='cuda')
+        Gp = torch.empty_like(G)
+        for p in range(P):
+            eng.gram_phase1([shards[p][0, k] for k in range(K)], N, mp, layout, meas_l[p], Gp)
+            G += Gp                                 # the all-reduce
+        P2 = torch.zeros((K, N * N + N + 4), dtype=torch.float64, device='cuda')
+        P2p = torch.empty_like(P2)
+        for p in range(P):
+            ptrs = [shards[p][0, k] for k in range(K)]
+            eng.gram_phase1(ptrs, N, mp, layout, meas_l[p], Gp)          # restores rank p's scratch
+            Gfull = G.clone()
+            eng.gram_phase2(ptrs, N, mp, layout, meas_l[p], var_l[p], m, Gfull, P2p, estimator=est)
+            P2 += P2p                               # the all-reduce
+        got = eng.gram_phase3(K, N, mp, G.clone(), P2)
+        for k in range(K):
+            assert abs(got[k] - want[k]) <= 1e-9 * max(1.0, abs(want[k])), (est, k, got[k], want[k])

@@ -76,3 +76,45 @@ def test_two_rank_gather_matches_single_process():
 def test_gather_rows_single_rank_is_identity():
     x = torch.arange(6.0).reshape(2, 3)
     assert gather_rows(x, 2) is x
+
+
+def _a2a_worker(rank, world, port, queue):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from imagine_b200.hotpath import exchange_pixel_shards, pixel_bounds
+    K, n_local, m = 2, 2, 12
+    mp = m // world
+    lo, hi = shard_bounds(world * n_local, rank, world)
+    # maps[k][r, pix] = 1000 k + 100 r_global + pix, written destination-major like the LOS kernel
+    send = torch.empty((world, K, n_local, mp), dtype=torch.float64)
+    for d in range(world):
+        for k in range(K):
+            for i in range(n_local):
+                send[d, k, i] = 1000 * k + 100 * (lo + i) + torch.arange(d * mp, (d + 1) * mp)
+    recv = exchange_pixel_shards(send)
+    plo, phi = pixel_bounds(m, rank, world)
+    queue.put((rank, recv.numpy(), plo, phi))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_pixel_shard_exchange():
+    """All-to-all of the destination-major LOS output: every rank ends with all realisations of its pixels."""
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_a2a_worker, args=(r, 2, port, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [queue.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, recv, plo, phi in results:
+        K, n_local = 2, 2
+        full = recv.transpose(1, 0, 2, 3).reshape(K, 2 * n_local, phi - plo)     # [K][N, m_local]
+        for k in range(K):
+            for r in range(2 * n_local):
+                assert np.array_equal(full[k, r], 1000 * k + 100 * r + np.arange(plo, phi))
