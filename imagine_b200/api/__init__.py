@@ -10,7 +10,7 @@ from ._bases import (Field, MagneticField, ThermalElectronDensityField,         
                      Simulations, Covariances, Masks, Simulator, Likelihood, BACKEND)
 
 from . import units                                                                    # noqa: F401
-from .device_observable import DeviceObservable                                        # noqa: F401
+from .device_observable import DeviceObservable, ShardedDeviceObservable                                        # noqa: F401
 from .fields import (ConstantMagneticField, NaiveGaussianMagneticField,                # noqa: F401
                      ConstantThermalElectrons, ExponentialThermalElectrons,
                      RandomThermalElectrons, CosThermalElectronDensity,

@@ -87,3 +87,87 @@ class DeviceObservable(Observable):
             import torch
             if torch.cuda.is_available():
                 self._tensor = torch.from_numpy(self._host).cuda()
+
+
+class ShardedDeviceObservable(Observable):
+    """
+    A simulated observable whose PIXELS are sharded over ranks: after the all-to-all of the
+    simulator's destination-major output this rank holds all N realisations of its m/P pixels,
+    as key `index` of the buffer `recv` [P(source), K, n_local, m/P].  `B200EnsembleLikelihood`
+    consumes it in place (phased Gram route, two small all-reduces).  Anything that needs the
+    full [N, m] block (`.tensor`, `.data`, masks, other likelihoods) triggers an all-gather --
+    a collective, so every rank must ask for it.
+    """
+
+    def __init__(self, recv, index, n_real, m, rank, world, group=None, unit=None, coords=None, otype=None):
+        self._dtype = 'simulated'
+        self.otype, self.unit, self.coords = otype, unit, coords
+        self._rw_flag = False
+        self.recv, self.index = recv, int(index)
+        self.n_real, self.m = int(n_real), int(m)
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self._full = None
+        self._host = None
+
+    # layout of the rows of this key inside `recv` (imb_gram_phase*): rows_per_block, strides
+    @property
+    def n_local(self):
+        return int(self.recv.shape[2])
+
+    @property
+    def m_local(self):
+        return int(self.recv.shape[3])
+
+    @property
+    def row_layout(self):
+        return (self.n_local, int(self.recv.shape[1]) * self.n_local * self.m_local, self.m_local)
+
+    @property
+    def base(self):
+        return self.recv[0, self.index]
+
+    @property
+    def pixel_bounds(self):
+        return self.rank * self.m_local, (self.rank + 1) * self.m_local
+
+    @property
+    def local_block(self):
+        """[N, m_local]: every realisation of this rank's pixels (copy)."""
+        return self.recv[:, self.index].reshape(self.n_real, self.m_local)
+
+    @property
+    def tensor(self):
+        if self._full is None:
+            import torch
+            import torch.distributed as dist
+            local = self.local_block.contiguous()
+            parts = torch.empty((self.world, self.n_real, self.m_local), dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(parts, local, group=self.group)
+            self._full = parts.permute(1, 0, 2).reshape(self.n_real, self.m).contiguous()
+        return self._full
+
+    @property
+    def data(self):
+        if self._host is None:
+            self._host = self.tensor.cpu().numpy()
+        return self._host
+
+    @data.setter
+    def data(self, value):
+        raise AttributeError('ShardedDeviceObservable is read-only')
+
+    global_data = property(lambda self: self.data)
+    shape = property(lambda self: (self.n_real, self.m))
+    size = property(lambda self: self.m)
+
+    @property
+    def ensemble_mean(self):
+        from .. import engine
+        return engine.ensemble_mean(self.tensor).cpu().numpy()
+
+    def append(self, new_data):
+        raise TypeError('ShardedDeviceObservable holds the whole ensemble; append is not supported')
+
+    def __getstate__(self):
+        raise TypeError('pixel-sharded observables are transient (one evaluation) and not picklable; '
+                        'pickle `.data` instead')

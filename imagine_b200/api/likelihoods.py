@@ -15,7 +15,7 @@ The simulated block may be a `DeviceObservable` (no copy) or a host `Observable`
 import numpy as np
 
 from ._bases import Likelihood, Simulations, Masks
-from .device_observable import DeviceObservable
+from .device_observable import DeviceObservable, ShardedDeviceObservable
 from .. import engine
 
 
@@ -45,6 +45,7 @@ class _DeviceLikelihoodMixin:
 
     def _reset_device_state(self):
         self._dev_meas, self._dev_cov, self._dev_keep = {}, {}, {}
+        self._shard_bufs = {}
 
     def _measured(self, key):
         if key not in self._dev_meas:
@@ -67,8 +68,8 @@ class _DeviceLikelihoodMixin:
         return c if c.dim() == 1 else c.diagonal().contiguous()
 
     def _block(self, obs):
-        if isinstance(obs, DeviceObservable):
-            return obs.tensor
+        if isinstance(obs, (DeviceObservable, ShardedDeviceObservable)):
+            return obs.tensor                       # sharded: all-gather (collective)
         return _torch().from_numpy(np.ascontiguousarray(obs.data, dtype=np.float64)).cuda()
 
     def _masked_simulations(self, observable_dict):
@@ -115,7 +116,7 @@ class _DeviceLikelihoodMixin:
 
     def __getstate__(self):
         state = dict(self.__dict__)
-        for k in ('_dev_meas', '_dev_cov', '_dev_keep'):
+        for k in ('_dev_meas', '_dev_cov', '_dev_keep', '_shard_bufs'):
             state[k] = {}
         return state
 
@@ -142,6 +143,10 @@ class B200EnsembleLikelihood(_DeviceLikelihoodMixin, Likelihood):
         assert isinstance(simulations_dict, Simulations)
         assert set(simulations_dict.keys()).issubset(self._measurement_dict.keys())
         assert set(simulations_dict.keys()).issubset(self._covariance_dict.keys())
+        gram_ok = (self.estimator in ('oas', 'empirical') and not self.use_trace_approximation
+                   and self.route in ('auto', 'gram'))
+        if gram_ok and self._all_pixel_sharded(simulations_dict):
+            return self._call_pixel_sharded(simulations_dict)
         # keys that may take the Gram route are evaluated in batches of identical [N, m]
         # (one launch sequence + one read-back per batch); the others go one by one
         names = list(simulations_dict.keys())
@@ -165,6 +170,43 @@ class B200EnsembleLikelihood(_DeviceLikelihoodMixin, Likelihood):
         total = 0.
         for name in names:                       # summed in dictionary order, like the reference
             total += values[name]
+        return total
+
+
+    # -- pixel-sharded ensembles (multi-rank): phased Gram route, two small all-reduces ----------------
+    def _all_pixel_sharded(self, simulations_dict):
+        obs = [simulations_dict[n] for n in simulations_dict]
+        if not obs or not all(isinstance(o, ShardedDeviceObservable) for o in obs):
+            return False
+        same = all(o.recv is obs[0].recv for o in obs)
+        variance = all(self._covariance_dict[n].dtype == 'variance' for n in simulations_dict)
+        return same and variance and len(obs) <= 16
+
+    def _call_pixel_sharded(self, simulations_dict):
+        import torch.distributed as dist
+        torch = _torch()
+        names = list(simulations_dict.keys())
+        obs = [simulations_dict[n] for n in names]
+        o0 = obs[0]
+        K, N, mp = len(obs), o0.n_real, o0.m_local
+        plo, phi = o0.pixel_bounds
+        meas = [self._measured(n)[plo:phi] for n in names]
+        var = [self._covariance(n)[plo:phi] for n in names]
+        sims = [o.base for o in obs]
+        key = (K, N)
+        if self._shard_bufs.get('key') != key:
+            self._shard_bufs = {'key': key,
+                                'G': torch.empty((K, N, N), dtype=torch.float64, device='cuda'),
+                                'P2': torch.empty((K, N * N + N + 4), dtype=torch.float64, device='cuda')}
+        G, P2 = self._shard_bufs['G'], self._shard_bufs['P2']
+        engine.gram_phase1(sims, N, mp, o0.row_layout, meas, G)
+        dist.all_reduce(G, op=dist.ReduceOp.SUM, group=o0.group)
+        engine.gram_phase2(sims, N, mp, o0.row_layout, meas, var, o0.m, G, P2, estimator=self.estimator)
+        dist.all_reduce(P2, op=dist.ReduceOp.SUM, group=o0.group)
+        vals = engine.gram_phase3(K, N, mp, G, P2)
+        total = 0.
+        for v in vals:
+            total += v
         return total
 
 

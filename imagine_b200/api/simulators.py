@@ -23,10 +23,10 @@ import numpy as np
 
 from . import units as u
 from ._bases import Simulator, Simulations
-from .device_observable import DeviceObservable
+from .device_observable import DeviceObservable, ShardedDeviceObservable
 from .fields import descriptor_of, device_grid
 from .. import engine
-from ..hotpath import gather_rows, shard_bounds
+from ..hotpath import exchange_pixel_shards, gather_rows, shard_bounds
 
 FIELD_UNITS = {'magnetic_field': u.microgauss, 'thermal_electron_density': u.cm ** -3}
 _NAMES = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
@@ -130,6 +130,8 @@ class B200Simulator(Simulator):
     cre_alpha, cre_beta, cre_theta, cre_E0 : CRE spectrum p = alpha - beta R - theta z at E0 [GeV]
                                         (fields/hamx/cre_analytic.py:19-27)
     rank, world, group : ensemble sharding over torch.distributed ranks (pipeline.py:737-744)
+    exchange : 'auto' | 'alltoall' | 'allgather' -- how the maps reach the likelihood on several ranks
+               (hotpath.py); 'alltoall' returns pixel-sharded observables
     """
     SIMULATED_QUANTITIES = ['fd', 'dm', 'sync']
     REQUIRED_FIELD_TYPES = ['magnetic_field']
@@ -138,8 +140,10 @@ class B200Simulator(Simulator):
 
     def __init__(self, measurements, observer=(-8.3, 0.0, 0.006), radial_step=0.1, radial_max=30.0,
                  cre_alpha=3.0, cre_beta=0.0, cre_theta=0.0, cre_E0=20.6, b_stride=16,
-                 rank=0, world=1, group=None):
+                 rank=0, world=1, group=None, exchange='auto'):
         super().__init__(measurements)
+        self.exchange = exchange
+        self._send = None
         self.los_kwargs = dict(observer=tuple(float(u.value_in(v, u.kpc)) for v in observer),
                                dr=float(u.value_in(radial_step, u.kpc)),
                                r_max=float(u.value_in(radial_max, u.kpc)),
@@ -185,8 +189,12 @@ class B200Simulator(Simulator):
         return self._dirs[nside]
 
     # -- the integrator for a block of realisations --------------------------------------------------
-    def _integrate(self, dg, fields, n_real):
-        """{key: tensor [n_real, m]} for every registered observable."""
+    def _integrate(self, dg, fields, n_real, sharded=None):
+        """
+        {key: tensor [n_real, m]} for every registered observable.  With `sharded = (views, layout)`
+        the LOS kernel writes each key straight into its slot of the destination-major send buffer
+        (views[key] = base pointer, layout = (cols_per_dest, dest_stride)); returns {}.
+        """
         torch = _torch()
         B = fields['magnetic_field']
         ne = fields.get('thermal_electron_density')
@@ -220,6 +228,13 @@ class B200Simulator(Simulator):
                 kw = dict(self.los_kwargs)
                 if freq is not None:
                     kw['nu_ghz'] = freq
+                if sharded is not None:
+                    views, layout = sharded
+                    out = {(k[0] if k[0] in ('fd', 'dm') else k[3]): views[k] for k in keys}
+                    engine.los_integrate(dg, engine.LosSettings(**kw), dirs, B, ne,
+                                         cre if want & {'I', 'Q', 'U'} else None, n_real=n_real,
+                                         want=tuple(want), out=out, out_layout=layout)
+                    continue
                 maps = engine.los_integrate(dg, engine.LosSettings(**kw), dirs, B, ne,
                                             cre if want & {'I', 'Q', 'U'} else None,
                                             n_real=n_real, want=tuple(want))
@@ -246,6 +261,8 @@ class B200Simulator(Simulator):
         if self._evaluator is None:
             self._evaluator = _DeviceFieldEvaluator(self.b_stride)
         dg, dev_fields = self._evaluator.evaluate(fields, self.grid, lo, hi)
+        if self._can_shard_pixels(dev_fields):
+            return self._call_pixel_sharded(dg, dev_fields, N, hi - lo)
         maps = self._integrate(dg, dev_fields, hi - lo)
         sims = Simulations()
         for key in self.observables:
@@ -255,6 +272,47 @@ class B200Simulator(Simulator):
             unit = self.output_units.get(key) or self._units(key)
             sims.append(name=key, data=DeviceObservable(block, unit, self.output_coords[key],
                                                         self.output_type[key]),
+                        coords=self.output_coords[key], otype=self.output_type[key])
+        return sims
+
+    # -- pixel-sharded exchange (multi-rank fast path) -------------------------------------------------
+    def _can_shard_pixels(self, dev_fields):
+        if self.world <= 1 or self.exchange not in ('auto', 'alltoall'):
+            return False
+        nsides = {int(k[2]) for k in self.observables}
+        direct = all(k[0] in ('fd', 'dm') or k[3] in ('I', 'Q', 'U') for k in self.observables)
+        per_real = any(t.dim() == 4 or t.shape[0] > 1 for t in dev_fields.values())
+        ok = len(nsides) == 1 and direct and per_real and (12 * nsides.pop() ** 2) % self.world == 0
+        if not ok and self.exchange == 'alltoall':
+            raise ValueError('exchange="alltoall" needs one Nside divisible over the ranks, only '
+                             'fd/dm/I/Q/U observables and at least one stochastic field')
+        return ok
+
+    def _call_pixel_sharded(self, dg, dev_fields, N, n_local):
+        """
+        The LOS kernel writes destination-major [P, K, n_local, m/P]; one all-to-all; the result is a
+        `Simulations` of `ShardedDeviceObservable`s that `B200EnsembleLikelihood` consumes in place.
+        """
+        torch = _torch()
+        K = len(self.observables)
+        m = 12 * int(self.observables[0][2]) ** 2
+        mp = m // self.world
+        shape = (self.world, K, n_local, mp)
+        if self._send is None or tuple(self._send.shape) != shape:
+            self._send = torch.empty(shape, dtype=torch.float64, device='cuda')
+        send = self._send
+        views = {key: send[0, k] for k, key in enumerate(self.observables)}
+        self._integrate(dg, dev_fields, n_local, sharded=(views, (mp, K * n_local * mp)))
+        recv = exchange_pixel_shards(send, self.group)
+        sims = Simulations()
+        for k, key in enumerate(self.observables):
+            s = self._scale(key)
+            if s != 1.0:
+                recv[:, k].mul_(s)
+            unit = self.output_units.get(key) or self._units(key)
+            sims.append(name=key,
+                        data=ShardedDeviceObservable(recv, k, N, m, self.rank, self.world, self.group, unit,
+                                                     self.output_coords[key], self.output_type[key]),
                         coords=self.output_coords[key], otype=self.output_type[key])
         return sims
 
@@ -285,6 +343,7 @@ class B200Simulator(Simulator):
         state = dict(self.__dict__)
         state['_dirs'] = {}
         state['_evaluator'] = None
+        state['_send'] = None
         state['_row_cache'] = (None, {})
         state['group'] = None
         return state

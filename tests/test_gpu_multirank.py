@@ -1,0 +1,114 @@
+"""
+GPU, >= 2 devices (skipped on a 1-GPU box): the N > 1 path over NCCL -- ensemble sharding, the
+destination-major LOS output + all-to-all, the phased Gram route with its two all-reduces, and the
+plugin drop-ins in pixel-sharded mode -- must reproduce the single-GPU numbers.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BOX = [[-20.0, 20.0], [-20.0, 20.0], [-4.0, 4.0]]
+QUANT = ('fd', 'dm', 'I', 'Q', 'U')
+DESCS = [(3, [0.01, 3.0, 0.5], 0), (0, [0.0, 1.0, 0.0], 1), (1, [0.0, 2.0], 2), (6, [0.0217, 5.0, 1.0, 8.3], 3)]
+N, NSIDE, RES = 8, 8, [24, 24, 12]
+
+
+def _setup(rank, world, exchange):
+    import torch
+    from imagine_b200 import engine
+    from imagine_b200.hotpath import EnsembleEvaluator
+    settings = engine.LosSettings(dr=0.25)
+    ev = EnsembleEvaluator(BOX, RES, NSIDE, settings, QUANT, n_real=N, rank=rank, world=world, exchange=exchange)
+    seeds = np.arange(1001, 1001 + N, dtype=np.uint64)
+    m = 12 * NSIDE ** 2
+    gen = torch.Generator(device='cpu').manual_seed(5)
+    meas = {q: (torch.randn(m, dtype=torch.float64, generator=gen) * s).cuda()
+            for q, s in zip(QUANT, (30.0, 100.0, 1e-4, 1e-4, 1e-4))}
+    var = {q: (torch.rand(m, dtype=torch.float64, generator=gen) + 0.5).cuda() * sc ** 2
+           for q, sc in zip(QUANT, (3.0, 10.0, 1e-5, 1e-5, 1e-5))}
+    return ev, seeds, meas, var
+
+
+def _plugin_value(rank, world):
+    import imagine_b200.api as api
+    u = api.units
+    m = 12 * NSIDE ** 2
+    ev, seeds, meas, var = _setup(0, 1, 'allgather')
+    grid = api.UniformGrid(box=[[b[0], b[1]] * u.kpc for b in BOX], resolution=RES)
+    keys = {'fd': ('fd', None, NSIDE, None), 'dm': ('dm', None, NSIDE, None), 'I': ('sync', 23.0, NSIDE, 'I'),
+            'Q': ('sync', 23.0, NSIDE, 'Q'), 'U': ('sync', 23.0, NSIDE, 'U')}
+    M = api.Measurements()
+    for q in QUANT:
+        M.append(name=keys[q], data=meas[q].cpu().numpy().reshape(1, m), cov_data=var[q].cpu().numpy(),
+                 otype='HEALPix')
+    sim = api.B200Simulator(M, radial_step=0.25, rank=rank, world=world)
+    lik = api.B200EnsembleLikelihood(M)
+    fields = [api.ExponentialThermalElectrons(grid, parameters={'central_density': 0.01 * u.cm ** -3,
+                                                                'scale_radius': 3 * u.kpc,
+                                                                'scale_height': 0.5 * u.kpc}, ensemble_size=N),
+              api.ConstantMagneticField(grid, parameters={'Bx': 0 * u.microgauss, 'By': 1 * u.microgauss,
+                                                          'Bz': 0 * u.microgauss}, ensemble_size=N),
+              api.NaiveGaussianMagneticField(grid, parameters={'a0': 0 * u.microgauss, 'b0': 2 * u.microgauss},
+                                             ensemble_size=N, ensemble_seeds=list(range(1001, 1001 + N))),
+              api.AnalyticCosmicRayElectrons(grid, parameters={'j0': 0.0217, 'r0': 5 * u.kpc, 'z0': 1 * u.kpc,
+                                                               'r_sun': 8.3 * u.kpc}, ensemble_size=N)]
+    sims = sim(fields)
+    return lik(sims), sims
+
+
+def _worker(rank, world, port, queue):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    from imagine_b200 import _lib
+    _lib.init(rank)
+    out = {}
+    for exchange in ('alltoall', 'allgather'):
+        ev, seeds, meas, var = _setup(rank, world, exchange)
+        out[exchange] = ev.evaluate(DESCS, seeds, meas, var)
+    value, sims = _plugin_value(rank, world)
+    out['plugin'] = value
+    key = ('sync', 23.0, NSIDE, 'Q')
+    out['plugin_sharded'] = type(sims[key]).__name__
+    out['plugin_full_Q'] = sims[key].data           # collective all-gather on every rank
+    queue.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_paths_match_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    from imagine_b200 import _lib
+    _lib.init(0)
+    ev, seeds, meas, var = _setup(0, 1, 'allgather')
+    want = ev.evaluate(DESCS, seeds, meas, var)
+    want_plugin, sims1 = _plugin_value(0, 1)
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [queue.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, out in results:
+        assert out['allgather'] == want                                   # bit-identical maps, same kernels
+        assert abs(out['alltoall'] - want) <= 1e-9 * max(1.0, abs(want))  # different summation order
+        assert out['plugin_sharded'] == 'ShardedDeviceObservable'
+        assert abs(out['plugin'] - want_plugin) <= 1e-9 * max(1.0, abs(want_plugin))
+        assert np.array_equal(out['plugin_full_Q'], sims1[('sync', 23.0, NSIDE, 'Q')].data)
+    assert results[0][1]['alltoall'] == results[1][1]['alltoall']         # replicated scalar
+    assert results[0][1]['plugin'] == results[1][1]['plugin']
