@@ -176,7 +176,7 @@ def main():
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--exchange', default='auto', choices=['auto', 'alltoall', 'allgather'])
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'peer', 'alltoall', 'allgather'])
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

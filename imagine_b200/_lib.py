@@ -45,7 +45,8 @@ class LosCfg(C.Structure):
     _fields_ = [('observer', C.c_double * 3), ('dr', C.c_double), ('n_steps', C.c_int32),
                 ('out_cols_per_dest', C.c_int32), ('nu_ghz', C.c_double), ('alpha', C.c_double),
                 ('beta', C.c_double), ('theta', C.c_double), ('e0_gev', C.c_double),
-                ('sync_k', C.c_double), ('out_dest_stride', C.c_int64)]
+                ('sync_k', C.c_double), ('out_dest_stride', C.c_int64), ('n_peers', C.c_int32),
+                ('reserved', C.c_int32), ('peer_delta', C.c_int64 * 16)]
 
 
 _P = C.c_void_p

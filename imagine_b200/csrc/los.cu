@@ -452,6 +452,13 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
     a.out_mp = cfg->out_cols_per_dest;
     a.out_dest = cfg->out_dest_stride;
   }
+  a.n_peers = 0;
+  if (cfg->n_peers > 0) {
+    if (cfg->n_peers > 16 || cfg->out_cols_per_dest <= 0 || m / cfg->out_cols_per_dest != cfg->n_peers)
+      return IMB_EINVAL;
+    a.n_peers = cfg->n_peers;
+    for (int d = 0; d < cfg->n_peers; ++d) a.peer_delta[d] = cfg->peer_delta[d];
+  }
   if (b_stride == 16 && has_ne && has_cre && rows_ne == 1 && rows_cre == 1) {
     // pack the two shared scalar grids into (n_e, CRE) pairs: one 128-bit gather per vertex
     IMB_TRY(ensure_workspace(sizeof(double) * 2 * (size_t)a.g.ncell + 256));

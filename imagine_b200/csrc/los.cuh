@@ -23,11 +23,17 @@ struct LosArgs {
   // exchange, [dest][...][n_real][out_mp] with `out_dest` doubles between destination blocks
   int out_mp;
   long long out_dest;
+  // fused exchange: destination d's block is written straight into rank d's receive buffer over
+  // NVLink; peer_delta[d] = (peer d's buffer base) - (my buffer base), in doubles
+  int n_peers;
+  long long peer_delta[16];
 };
 
 __device__ __forceinline__ long long out_index(const LosArgs& a, int rr, int pix) {
   const int dest = pix / a.out_mp;
-  return (long long)dest * a.out_dest + (long long)rr * a.out_mp + (pix - dest * a.out_mp);
+  const long long within = (long long)rr * a.out_mp + (pix - dest * a.out_mp);
+  if (a.n_peers > 0) return a.peer_delta[dest] + within;
+  return (long long)dest * a.out_dest + within;
 }
 
 __device__ __forceinline__ double4 ldg256(const double* p) {

@@ -55,9 +55,13 @@ class LosSettings:
         return LosSettings(self.observer, self.dr, None, self.n_steps, nu_ghz, self.alpha,
                            self.beta, self.theta, self.e0_gev)
 
-    def c_struct(self, out_cols_per_dest=0, out_dest_stride=0):
+    def c_struct(self, out_cols_per_dest=0, out_dest_stride=0, peer_delta=None):
         cfg = L.LosCfg()
         cfg.out_cols_per_dest, cfg.out_dest_stride = int(out_cols_per_dest), int(out_dest_stride)
+        if peer_delta is not None:
+            cfg.n_peers = len(peer_delta)
+            for d, v in enumerate(peer_delta):
+                cfg.peer_delta[d] = int(v)
         for a in range(3):
             cfg.observer[a] = self.observer[a]
         cfg.dr, cfg.n_steps, cfg.nu_ghz = self.dr, self.n_steps, self.nu_ghz
@@ -162,7 +166,9 @@ def los_integrate(grid, settings, dirs, B, ne=None, cre=None, n_real=1,
     Integrate every realisation along `dirs` [m,3] (imb_los_integrate).  Returns a dict of
     [n_real, m] tensors for the requested quantities.  With `out_layout = (cols_per_dest,
     dest_stride)` the tensors in `out` are base pointers of a pixel-sharded send buffer
-    (pixel p of realisation r at (p // cols) * dest_stride + r * cols + p % cols).
+    (pixel p of realisation r at (p // cols) * dest_stride + r * cols + p % cols); a third entry
+    `peer_delta` (list of P offsets in doubles) switches on the fused NVLink exchange, where the
+    block of destination d lands directly in rank d's symmetric receive buffer.
     """
     torch = _torch()
     L.init()

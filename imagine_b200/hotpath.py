@@ -15,6 +15,11 @@ Two exchange modes between the simulation and the likelihood:
               SUM all-reduces in between (G: K*N*N doubles, P2: K*(N*N+N+4) doubles) -- the
               exchange the reference does with mpi4py Allreduce / ring matmul
               (tools/mpi_helper.py:132, 234-246).  The likelihood work is sharded P ways.
+  'peer'      Same data flow as 'alltoall', but the collective is FUSED into the LOS kernel: the
+              receive buffer is NVLink symmetric memory (torch.distributed._symmetric_memory) and
+              the kernel's epilogue stores the block of destination rank d straight into rank d's
+              buffer (peer stores, `imb_los_cfg.peer_delta`), overlapping the exchange with the
+              ray march; a signal-pad barrier replaces the all-to-all.  'auto' tries this first.
   'allgather' Every rank receives every realisation's full maps (one all-gather per observable)
               and evaluates the likelihood redundantly; what the plugin API needs, since
               `Simulations` must expose the full [N, m] block.
@@ -94,16 +99,29 @@ class EnsembleEvaluator:
         self.dirs = engine.healpix_ring_dirs(self.nside)
         self._field_bufs = {}
         dev = self.dirs.device
+        shardable = self.world > 1 and self.m % self.world == 0 and self.world <= 16
         if exchange == 'auto':
-            exchange = 'alltoall' if (self.world > 1 and self.m % self.world == 0) else 'allgather'
-        self.exchange = exchange
+            exchange = 'peer' if shardable else 'allgather'
+            auto = True
+        else:
+            auto = False
         f64 = torch.float64
-        if self.exchange == 'alltoall':
+        self._symm = None
+        if exchange == 'peer':
+            try:
+                self._init_peer_buffers(dev)
+            except Exception:
+                if not auto:
+                    raise
+                exchange = 'alltoall'               # symmetric memory unavailable: NCCL all-to-all
+        self.exchange = exchange
+        if self.exchange in ('alltoall', 'peer'):
             self.mp = self.m // self.world
             self.plo, self.phi = pixel_bounds(self.m, self.rank, self.world)
-            # destination-major send buffer the LOS kernel writes into; recv after the all-to-all
-            self.send = torch.empty((self.world, self.K, self.n_local, self.mp), dtype=f64, device=dev)
-            self.recv = self.send if self.world == 1 else torch.empty_like(self.send)
+            if self.exchange == 'alltoall':
+                # destination-major send buffer the LOS kernel writes into; recv after the all-to-all
+                self.send = torch.empty((self.world, self.K, self.n_local, self.mp), dtype=f64, device=dev)
+                self.recv = self.send if self.world == 1 else torch.empty_like(self.send)
             self.G = torch.empty((self.K, self.n_real, self.n_real), dtype=f64, device=dev)
             self.P2 = torch.empty((self.K, self.n_real * self.n_real + self.n_real + 4), dtype=f64, device=dev)
             self.local_maps = None
@@ -115,6 +133,22 @@ class EnsembleEvaluator:
                                   for q in self.quantities}
             else:
                 self.full_maps = self.local_maps
+
+    def _init_peer_buffers(self, dev):
+        """Receive buffer [P(source), K, n_local, m/P] in NVLink symmetric memory + peer offsets."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        torch = self.torch
+        mp = self.m // self.world
+        self.recv = symm_mem.empty((self.world, self.K, self.n_local, mp), dtype=torch.float64, device=dev)
+        group = self.group if self.group is not None else dist.group.WORLD
+        self._symm = symm_mem.rendezvous(self.recv, group.group_name)
+        ptrs = [int(p) for p in self._symm.buffer_ptrs]
+        mine = ptrs[self.rank]
+        assert mine == self.recv.data_ptr()
+        assert all((p - mine) % 8 == 0 for p in ptrs)
+        self.peer_delta = [(p - mine) // 8 for p in ptrs]
+        self.send = None
 
     # -- stage 1 + 2 -----------------------------------------------------------------------
     def fields(self, descs, seeds):
@@ -138,6 +172,10 @@ class EnsembleEvaluator:
         if self.exchange == 'alltoall':
             out = {LOS_OUTPUT[q]: self.send[0, k] for k, q in enumerate(self.quantities)}
             layout = (self.mp, self.K * self.n_local * self.mp)
+        elif self.exchange == 'peer':
+            # my source slot inside MY receive buffer; the kernel redirects each pixel block to its owner
+            out = {LOS_OUTPUT[q]: self.recv[self.rank, k] for k, q in enumerate(self.quantities)}
+            layout = (self.mp, 0, self.peer_delta)
         else:
             out = {LOS_OUTPUT[q]: self.local_maps[q] for q in self.quantities}
             layout = None
@@ -149,11 +187,14 @@ class EnsembleEvaluator:
     def simulate(self, descs, seeds):
         """Run fields + LOS for this rank's block of realisations (outputs stay in device buffers)."""
         self.los(self.fields(descs, seeds))
-        return self.local_maps if self.exchange == 'allgather' else self.send
+        return self.local_maps if self.exchange == 'allgather' else (self.send if self.send is not None else self.recv)
 
     # -- exchange ----------------------------------------------------------------------------
     def gather(self):
         """Move the simulated maps to where the likelihood needs them."""
+        if self.exchange == 'peer':
+            self._symm.barrier()                    # every rank's LOS kernel (and its peer stores) is done
+            return self.recv
         if self.exchange == 'alltoall':
             if self.world > 1:
                 import torch.distributed as dist
@@ -175,7 +216,7 @@ class EnsembleEvaluator:
     def loglike(self, maps, meas, var, estimator='oas'):
         """Sum over observables of EnsembleLikelihood's per-key term (diagonal measurement cov)."""
         qs = self.quantities
-        if self.exchange == 'alltoall':
+        if self.exchange in ('alltoall', 'peer'):
             sims = [maps[0, k] for k in range(self.K)]        # base pointer of key k, blocked rows
             layout = (self.n_local, self.K * self.n_local * self.mp, self.mp)
             meas_l = [meas[q][self.plo:self.phi] for q in qs]

@@ -83,6 +83,13 @@ typedef struct {
   double e0_gev;       /* CRE reference energy [GeV]                                      */
   double sync_k;       /* K(alpha,nu) computed by the host when beta == theta == 0        */
   int64_t out_dest_stride;   /* doubles between destination blocks (see out_cols_per_dest)  */
+  /* Fused exchange (optional): with n_peers = m / out_cols_per_dest > 0 the block of destination */
+  /* d is stored straight into rank d's buffer over NVLink peer memory: the out_* pointers address */
+  /* MY slot inside my own (symmetric) receive buffer and peer_delta[d] = (rank d's buffer base -  */
+  /* mine) in doubles is added for pixels owned by d.  out_dest_stride is ignored.                 */
+  int32_t n_peers;
+  int32_t reserved;
+  int64_t peer_delta[16];
 } imb_los_cfg;
 
 /* ---- likelihood options ------------------------------------------------------------ */

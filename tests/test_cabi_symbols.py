@@ -53,4 +53,4 @@ def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_lib.Grid) == 64
     assert C.sizeof(_lib.FieldDesc) == 80
-    assert C.sizeof(_lib.LosCfg) == 96
+    assert C.sizeof(_lib.LosCfg) == 232

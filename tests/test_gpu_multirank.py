@@ -69,7 +69,7 @@ def _worker(rank, world, port, queue):
     from imagine_b200 import _lib
     _lib.init(rank)
     out = {}
-    for exchange in ('alltoall', 'allgather'):
+    for exchange in ('peer', 'alltoall', 'allgather'):
         ev, seeds, meas, var = _setup(rank, world, exchange)
         out[exchange] = ev.evaluate(DESCS, seeds, meas, var)
     value, sims = _plugin_value(rank, world)
@@ -107,6 +107,7 @@ def test_two_gpu_paths_match_single_gpu():
     for rank, out in results:
         assert out['allgather'] == want                                   # bit-identical maps, same kernels
         assert abs(out['alltoall'] - want) <= 1e-9 * max(1.0, abs(want))  # different summation order
+        assert out['peer'] == out['alltoall']                             # fused NVLink exchange: same data, same kernels
         assert out['plugin_sharded'] == 'ShardedDeviceObservable'
         assert abs(out['plugin'] - want_plugin) <= 1e-9 * max(1.0, abs(want_plugin))
         assert np.array_equal(out['plugin_full_Q'], sims1[('sync', 23.0, NSIDE, 'Q')].data)
