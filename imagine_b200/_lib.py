@@ -17,7 +17,7 @@ IMB_OK, IMB_EINVAL, IMB_ECUDA, IMB_ENOMEM, IMB_ENOTINIT, IMB_EBOUNDS, IMB_ESINGU
 
 # field kinds (include/imagine_b200.h)
 (FIELD_CONST_B, FIELD_GAUSS_B, FIELD_CONST_NE, FIELD_EXP_NE, FIELD_COS_NE, FIELD_RANDOM_NE,
- FIELD_CRE_ANALYTIC, FIELD_CRE_CONST) = range(8)
+ FIELD_CRE_ANALYTIC, FIELD_CRE_CONST, FIELD_LSA_B) = range(9)
 COV_NONE, COV_VARIANCE, COV_DENSE = range(3)
 EST_EMPIRICAL, EST_OAS, EST_DIAGONAL = range(3)
 ROUTE_AUTO, ROUTE_GRAM, ROUTE_DENSE = range(3)

@@ -11,7 +11,7 @@ from ._bases import (Field, MagneticField, ThermalElectronDensityField,         
 
 from . import units                                                                    # noqa: F401
 from .device_observable import DeviceObservable, ShardedDeviceObservable                                        # noqa: F401
-from .fields import (ConstantMagneticField, NaiveGaussianMagneticField,                # noqa: F401
+from .fields import (ConstantMagneticField, NaiveGaussianMagneticField, LSAMagneticField,                # noqa: F401
                      ConstantThermalElectrons, ExponentialThermalElectrons,
                      RandomThermalElectrons, CosThermalElectronDensity,
                      AnalyticCosmicRayElectrons, ConstantCosmicRayElectrons)

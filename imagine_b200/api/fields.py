@@ -100,6 +100,25 @@ class NaiveGaussianMagneticField(_DeviceFieldMixin, MagneticField):
     KIND = L.FIELD_GAUSS_B
 
 
+class LSAMagneticField(_DeviceFieldMixin, MagneticField):
+    """
+    WMAP-3yr logarithmic-spiral-arm regular field evaluated on the grid: the gridded counterpart of
+    the `BregLSA` dummy (fields/hamx/breg_lsa.py:11-31: NAME 'breg_lsa', parameters b0 [uG],
+    psi0, psi1, chi0 [deg]) -- the 4-parameter GMF model of BASELINE config 5.
+    """
+    NAME = 'breg_lsa'
+    PARAMETER_NAMES = ['b0', 'psi0', 'psi1', 'chi0']
+    PARAM_UNITS = (u.microgauss, u.deg, u.deg, u.deg)
+    KIND = L.FIELD_LSA_B
+    R0_KPC, Z0_KPC, R_MIN_KPC, R_MAX_KPC = 8.0, 1.0, 3.0, 20.0
+
+    def _canonical_parameters(self):
+        b0, psi0, psi1, chi0 = super()._canonical_parameters()       # plain numbers are degrees
+        d2r = np.pi / 180.0
+        return [b0, psi0 * d2r, psi1 * d2r, chi0 * d2r, self.R0_KPC, self.Z0_KPC, self.R_MIN_KPC,
+                self.R_MAX_KPC]
+
+
 class ConstantThermalElectrons(_DeviceFieldMixin, ThermalElectronDensityField):
     NAME = 'constant_TE'
     PARAMETER_NAMES = ['ne']

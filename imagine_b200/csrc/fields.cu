@@ -32,6 +32,38 @@ __device__ __forceinline__ void cell_xyz(const DevGrid& g, long long c, double& 
   z = vertex_coord(g, 2, iz);
 }
 
+// WMAP-3yr logarithmic spiral arm field (the model hammurabiX's `breg_lsa` implements; the
+// reference only routes its four parameters to the binary, fields/hamx/breg_lsa.py:20-31):
+//   psi = psi0 + psi1 ln(R/r0), chi = chi0 tanh(z/z0), zero outside r_min < R < r_max,
+//   B = b0 (sin psi cos chi R^ + cos psi cos chi phi^ + sin chi z^)
+//   p = b0 [uG], psi0, psi1, chi0 [rad], r0, z0, r_min, r_max [kpc]
+__device__ __forceinline__ void lsa_field(const double* p, double x, double y, double z, double* b) {
+  const double R = sqrt(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+  if (!(R > p[6]) || !(R < p[7])) { b[0] = b[1] = b[2] = 0.0; return; }
+  const double cp = x / R, sp = y / R;
+  const double psi = __dadd_rn(p[1], __dmul_rn(p[2], log(R / p[4])));
+  const double chi = __dmul_rn(p[3], tanh(z / p[5]));
+  const double cc = cos(chi);
+  const double br = __dmul_rn(__dmul_rn(p[0], sin(psi)), cc);
+  const double bphi = __dmul_rn(__dmul_rn(p[0], cos(psi)), cc);
+  b[0] = __dsub_rn(__dmul_rn(br, cp), __dmul_rn(bphi, sp));
+  b[1] = __dadd_rn(__dmul_rn(br, sp), __dmul_rn(bphi, cp));
+  b[2] = __dmul_rn(p[0], sin(chi));
+}
+
+__device__ __forceinline__ void lsa_pair(const DevGrid& g, const double* p, long long c0, bool has2,
+                                         double* t) {
+  double x, y, z;
+  cell_xyz(g, c0, x, y, z);
+  lsa_field(p, x, y, z, t);
+  if (has2) {
+    cell_xyz(g, c0 + 1, x, y, z);
+    lsa_field(p, x, y, z, t + 3);
+  } else {
+    t[3] = t[4] = t[5] = 0.0;
+  }
+}
+
 // ---- magnetic field: [rows, ncell, BS] ------------------------------------------------
 template <int BS, bool VEC>
 __global__ void __launch_bounds__(256) field_b_kernel(const __grid_constant__ FieldArgs a,
@@ -49,6 +81,8 @@ __global__ void __launch_bounds__(256) field_b_kernel(const __grid_constant__ Fi
       if (a.kind[f] == IMB_FIELD_CONST_B) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) t[k] = a.p[f][k % 3];
+      } else if (a.kind[f] == IMB_FIELD_LSA_B) {
+        lsa_pair(a.g, a.p[f], 2 * q, (2 * q + 1) < a.g.ncell, t);
       } else {  // IMB_FIELD_GAUSS_B: flat normal index n = 3*cell + comp, block n >> 1
         const unsigned long long seed = a.seeds[(size_t)a.seed_row[f] * a.n_real + r];
         const double mu = a.p[f][0], sigma = a.p[f][1];
@@ -110,6 +144,8 @@ __global__ void __launch_bounds__(256) field_b_il4_kernel(const __grid_constant_
         if (a.kind[f] == IMB_FIELD_CONST_B) {
 #pragma unroll
           for (int k = 0; k < 6; ++k) t[k] = a.p[f][k % 3];
+        } else if (a.kind[f] == IMB_FIELD_LSA_B) {
+          lsa_pair(a.g, a.p[f], 2ll * q, (2ll * q + 1) < a.g.ncell, t);
         } else {
           const unsigned long long seed = a.seeds[(size_t)a.seed_row[f] * a.n_real + r];
           const double mu = a.p[f][0], sigma = a.p[f][1];
@@ -324,7 +360,7 @@ int make_dev_grid(const imb_grid* grid, DevGrid* g) {
 
 static int field_type(int kind) {
   switch (kind) {
-    case IMB_FIELD_CONST_B: case IMB_FIELD_GAUSS_B: return 0;
+    case IMB_FIELD_CONST_B: case IMB_FIELD_GAUSS_B: case IMB_FIELD_LSA_B: return 0;
     case IMB_FIELD_CONST_NE: case IMB_FIELD_EXP_NE: case IMB_FIELD_COS_NE:
     case IMB_FIELD_RANDOM_NE: return 1;
     case IMB_FIELD_CRE_ANALYTIC: case IMB_FIELD_CRE_CONST: return 2;

@@ -58,7 +58,9 @@ enum {
   IMB_FIELD_COS_NE = 4,       /* p = n0,a,alpha,b,beta,c,gamma  test_field.py:36-43       */
   IMB_FIELD_RANDOM_NE = 5,    /* p = mean,std,min_ne, stochastic basic_fields.py:111-127  */
   IMB_FIELD_CRE_ANALYTIC = 6, /* p = j0,r0,z0,r_sun   (new: base_fields.py:104-113 stub;  */
-  IMB_FIELD_CRE_CONST = 7     /* p = j0                parameter names hamx/cre_analytic) */
+  IMB_FIELD_CRE_CONST = 7,    /* p = j0                parameter names hamx/cre_analytic) */
+  IMB_FIELD_LSA_B = 8         /* p = b0 [uG], psi0, psi1, chi0 [rad], r0, z0, r_min, r_max [kpc]:  */
+                              /* WMAP-3yr logarithmic spiral (parameter names hamx/breg_lsa.py:20-31) */
 };
 #define IMB_MAX_FIELDS 16
 

@@ -24,13 +24,13 @@ used for the CPU baseline timing and the distribution checks.
 import numpy as np
 
 # field kinds -- must match include/imagine_b200.h (IMB_FIELD_*)
-CONST_B, GAUSS_B, CONST_NE, EXP_NE, COS_NE, RANDOM_NE, CRE_ANALYTIC, CRE_CONST = range(8)
+CONST_B, GAUSS_B, CONST_NE, EXP_NE, COS_NE, RANDOM_NE, CRE_ANALYTIC, CRE_CONST, LSA_B = range(9)
 
 TYPE_OF_KIND = {CONST_B: 'magnetic_field', GAUSS_B: 'magnetic_field',
                 CONST_NE: 'thermal_electron_density', EXP_NE: 'thermal_electron_density',
                 COS_NE: 'thermal_electron_density', RANDOM_NE: 'thermal_electron_density',
                 CRE_ANALYTIC: 'cosmic_ray_electron_density',
-                CRE_CONST: 'cosmic_ray_electron_density'}
+                CRE_CONST: 'cosmic_ray_electron_density', LSA_B: 'magnetic_field'}
 STOCHASTIC_KINDS = (GAUSS_B, RANDOM_NE)
 
 
@@ -100,6 +100,27 @@ def cre_analytic(grid, j0, r0, z0, r_sun):
     R = np.sqrt(x**2 + y**2)
     ch = np.cosh(z / z0)
     return j0 * np.exp(-(R - r_sun) / r0) * (1.0 / (ch * ch)) * np.ones(grid.shape)
+
+
+def lsa_B(grid, b0, psi0, psi1, chi0, r0=8.0, z0=1.0, r_min=3.0, r_max=20.0):
+    """
+    WMAP-3yr logarithmic-spiral-arm regular field (Page et al. 2007), the model behind
+    hammurabiX's `breg_lsa`; the reference only forwards (b0, psi0, psi1, chi0) to the binary
+    (fields/hamx/breg_lsa.py:20-31), so like the LOS integrator this is defined here, unpinned.
+    Angles in rad.  B = b0 (sin psi cos chi R^ + cos psi cos chi phi^ + sin chi z^),
+    psi = psi0 + psi1 ln(R/r0), chi = chi0 tanh(z/z0); zero outside r_min < R < r_max.
+    """
+    x, y, z = (v * np.ones(grid.shape) for v in grid.xyz())
+    R = np.sqrt(x**2 + y**2)
+    ok = (R > r_min) & (R < r_max)
+    Rs = np.where(ok, R, 1.0)
+    cp, sp = x / Rs, y / Rs
+    psi = psi0 + psi1 * np.log(Rs / r0)
+    chi = chi0 * np.tanh(z / z0)
+    cc = np.cos(chi)
+    br, bphi = b0 * np.sin(psi) * cc, b0 * np.cos(psi) * cc
+    out = np.stack([br * cp - bphi * sp, br * sp + bphi * cp, b0 * np.sin(chi)], axis=-1)
+    return np.where(ok[..., None], out, 0.0)
 
 
 def cre_const(grid, j0):
@@ -229,6 +250,8 @@ def evaluate_fields(grid, descs, seeds, rng='philox'):
                 seeds = seed_table[row]
                 if kind == CONST_B:
                     f = constant_B(grid, *p[:3])
+                elif kind == LSA_B:
+                    f = lsa_B(grid, *p[:8])
                 elif kind == GAUSS_B:
                     f = (gaussian_B_philox(grid, p[0], p[1], seeds[r], stream) if rng == 'philox'
                          else gaussian_B_reference(grid, p[0], p[1], seeds[r]))

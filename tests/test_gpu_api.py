@@ -265,3 +265,23 @@ def test_gpu_fields_serve_host_consumers(api):
     assert a.shape == (15, 15, 15, 3) and not np.array_equal(a.value, b.value)
     assert np.array_equal(g.get_data(0).value, a.value)
     assert abs(a.value.mean() - 3) < 0.5 and abs(a.value.std() - 6) < 0.5
+
+
+def test_four_parameter_lsa_fit_prefers_the_truth(api):
+    """configs[4] in miniature: the drop-ins behind a sampler-style loglike(theta) callback."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'examples', 'gmf_fit_lsa.py')
+    spec = importlib.util.spec_from_file_location('gmf_fit_lsa', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    loglike = mod.build(grid_n=32, nside=8, n_ens=8, noise=0.05)
+    truth = loglike([6.0, 27.0, 0.9, 25.0])
+    assert np.isfinite(truth)
+    assert loglike([6.0, 27.0, 0.9, 25.0]) == truth                  # deterministic given the seeds
+    for theta in ([4.0, 27.0, 0.9, 25.0], [6.0, 10.0, 0.9, 25.0], [6.0, 27.0, 0.9, -10.0]):
+        assert loglike(theta) < truth
+    assert loglike([11.0, 27.0, 0.9, 25.0]) == -np.inf               # outside the prior box
+    chain, acc = mod.metropolis(loglike, [5.5, 25.0, 1.0, 22.0], 30, np.array([0.05, 0.3, 0.05, 0.5]),
+                                np.random.default_rng(0))
+    assert chain.shape == (30, 4) and 0.0 <= acc <= 1.0

@@ -142,3 +142,25 @@ def test_template_golden_end_to_end_on_gpu(eng):
     meas = torch.ones(5, dtype=torch.float64).cuda()
     var = torch.full((5,), 0.1 ** 2, dtype=torch.float64).cuda()
     assert eng.loglike_simple(sims, meas, var) == pytest.approx(-55.581767201053125, abs=1e-11)
+
+
+@pytest.mark.parametrize('bs', [3, 4])
+def test_lsa_field_matches_oracle(eng, bs):
+    """WMAP LSA regular field (gridded counterpart of hamx/breg_lsa.py), summed with a constant field."""
+    p = [6.0, np.radians(27.0), np.radians(0.9), np.radians(25.0), 8.0, 1.0, 3.0, 20.0]
+    descs = [(OF.LSA_B, p, 0), (OF.CONST_B, [0.1, 0.0, -0.2], 0)]
+    for res in ([33, 31, 9], [16, 16, 8]):
+        got = _gpu_fields(eng, BOX, res, descs, [1], bs)['magnetic_field']
+        want = OF.evaluate_fields(OF.Grid(BOX, res), descs, [1])['magnetic_field']
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-12)
+    og = OF.Grid(BOX, [33, 31, 9])
+    B = OF.lsa_B(og, *p)
+    x, y, z = (v * np.ones(og.shape) for v in og.xyz())
+    R = np.sqrt(x ** 2 + y ** 2)
+    inside = (R > 3.0) & (R < 20.0)
+    assert np.allclose(np.linalg.norm(B, axis=-1)[inside], 6.0, rtol=1e-12)      # |B| = b0 in the annulus
+    assert np.all(B[~inside] == 0.0)
+    br = (B[..., 0] * x + B[..., 1] * y)[inside] / R[inside]                      # pitch angle psi(R) at z = 0
+    mid = np.abs(z[inside]) < 1e-9
+    psi = np.radians(27.0) + np.radians(0.9) * np.log(R[inside][mid] / 8.0)
+    assert np.allclose(br[mid], 6.0 * np.sin(psi), rtol=1e-10)
