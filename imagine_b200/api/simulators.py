@@ -402,3 +402,26 @@ class B200TestSimulator(Simulator):
         row = engine.test_simulate(dg, torch.from_numpy(B).cuda(), torch.from_numpy(ne).cuda(), 1,
                                    self._points(coords_dict), b_axis=self.B_axis, scale=scale)
         return row[0].cpu().numpy() * (output_units if output_units is not None else native)
+
+
+def dump_hammurabi_fields(fields, directory, prefix=''):
+    """
+    hammurabiX-compatible field I/O (simulators/hammurabi.py:229-273): every field type as raw
+    C-order float64 (`ndarray.tofile`), one file per type named like the XML `fieldio` entries
+    (breg / tereg / cre), plus the box / vertex-count keys the wrapper copies into the XML.  Lets a
+    real hammurabiX install elsewhere integrate the very same grids for an external cross-check of
+    the LOS definition.  `fields` = {field_type: Quantity or ndarray [nx,ny,nz(,3)]} for ONE
+    realisation (e.g. `simulator.fields` after `prepare_fields`); returns {hamx_key: (path, meta)}.
+    """
+    import os
+    names = {'magnetic_field': 'breg', 'thermal_electron_density': 'tereg',
+             'cosmic_ray_electron_density': 'cre'}
+    out = {}
+    for ftype, data in fields.items():
+        if ftype not in names:
+            continue
+        arr = np.ascontiguousarray(_host_values(data, FIELD_UNITS.get(ftype)), dtype=np.float64)
+        path = os.path.join(directory, '%s%s.bin' % (prefix, names[ftype]))
+        arr.tofile(path)
+        out[names[ftype]] = (path, {'nx': arr.shape[0], 'ny': arr.shape[1], 'nz': arr.shape[2]})
+    return out

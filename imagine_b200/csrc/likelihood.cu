@@ -525,8 +525,9 @@ int imb_loglike_simple(const double* sims, int N, int m, const double* meas, con
 int imb_gather_columns(const double* in, int rows, int m, const int32_t* idx, int m_out, double* out,
                        void* stream) {
   IMB_TRY(check_init());
-  if (!in || !idx || !out || rows < 0 || m_out < 0) return IMB_EINVAL;
+  if (rows < 0 || m_out < 0) return IMB_EINVAL;
   if (rows == 0 || m_out == 0) return IMB_OK;
+  if (!in || !idx || !out) return IMB_EINVAL;
   gather_columns_kernel<<<grid_blocks((long long)rows * m_out, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       in, rows, m, idx, m_out, out);
   IMB_LAUNCHED();
@@ -535,8 +536,9 @@ int imb_gather_columns(const double* in, int rows, int m, const int32_t* idx, in
 
 int imb_gather_cov(const double* cov, int m, const int32_t* idx, int m_out, double* out, void* stream) {
   IMB_TRY(check_init());
-  if (!cov || !idx || !out || m_out < 0) return IMB_EINVAL;
+  if (m_out < 0) return IMB_EINVAL;
   if (m_out == 0) return IMB_OK;
+  if (!cov || !idx || !out) return IMB_EINVAL;
   gather_cov_kernel<<<grid_blocks((long long)m_out * m_out, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       cov, m, idx, m_out, out);
   IMB_LAUNCHED();

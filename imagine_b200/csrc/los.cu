@@ -398,6 +398,7 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
   IMB_TRY(check_init());
   LosArgs a;
   IMB_TRY(make_dev_grid(grid, &a.g));
+  if (m == 0 && cfg && n_real >= 1) return IMB_OK;            // nothing to integrate
   if (!cfg || !dirs || !B || m < 0 || n_real < 1) return IMB_EINVAL;
   if (b_stride != 3 && b_stride != 4 && b_stride != 16) return IMB_EINVAL;
   if (b_stride >= 4 && (reinterpret_cast<uintptr_t>(B) % 32 != 0)) return IMB_EINVAL;

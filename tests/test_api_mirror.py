@@ -174,3 +174,15 @@ def test_gpu_field_descriptors_without_gpu():
                                                       'c': 0 * u.rad / u.kpc, 'gamma': np.pi / 2})
     assert c.device_descriptor()[1] == pytest.approx([1, 1, 0, 0, np.pi / 2, 0, np.pi / 2])
     pickle.loads(pickle.dumps(g))                            # checkpointable (io.py:25-75)
+
+
+def test_hammurabi_field_dump_layout(tmp_path):
+    """Raw C-order float64, component innermost: the format hammurabi.py:267 writes with tofile."""
+    from imagine_b200.api.simulators import dump_hammurabi_fields
+    B = np.arange(2 * 3 * 4 * 3, dtype=np.float64).reshape(2, 3, 4, 3) * u.microgauss
+    ne = np.arange(24, dtype=np.float64).reshape(2, 3, 4) * u.cm ** -3
+    out = dump_hammurabi_fields({'magnetic_field': B, 'thermal_electron_density': ne, 'dummy': {}}, str(tmp_path))
+    assert set(out) == {'breg', 'tereg'}
+    back = np.fromfile(out['breg'][0], dtype=np.float64)
+    assert np.array_equal(back, np.arange(72.0)) and out['breg'][1] == {'nx': 2, 'ny': 3, 'nz': 4}
+    assert np.array_equal(np.fromfile(out['tereg'][0]), np.arange(24.0))

@@ -89,7 +89,8 @@ def test_c3_likelihood_gram_vs_numpy_gram_and_sharding_invariance(c3):
     # simulating the ensemble in two halves (what 2 ranks do) gives bit-identical maps
     from imagine_b200.hotpath import EnsembleEvaluator
     for rank in (0, 1):
-        half = EnsembleEvaluator(BOX, [128] * 3, 64, ev.settings, n_real=64, rank=rank, world=2)
+        half = EnsembleEvaluator(BOX, [128] * 3, 64, ev.settings, n_real=64, rank=rank, world=2,
+                                 exchange='allgather')
         local = half.simulate(DESCS, seeds)
         for q in maps:
             assert torch.equal(local[q], maps[q][rank * 32:(rank + 1) * 32]), (rank, q)

@@ -267,3 +267,22 @@ def test_phased_gram_route_over_pixel_shards(eng, N, m, K, P):
         got = eng.gram_phase3(K, N, mp, G.clone(), P2)
         for k in range(K):
             assert abs(got[k] - want[k]) <= 1e-9 * max(1.0, abs(want[k])), (est, k, got[k], want[k])
+
+
+def test_edge_shapes(eng):
+    """Smallest / ragged inputs: one pixel, one realisation, empty masks, N >> m."""
+    import torch
+    rng = np.random.default_rng(8)
+    for N, m in [(1, 1), (2, 1), (5, 1), (1, 7), (70, 3)]:
+        sims, meas, var = rng.normal(size=(N, m)), rng.normal(size=m), rng.uniform(0.5, 1.5, m)
+        want = OK.ensemble_loglike(sims, meas, var)
+        assert abs(eng.loglike_ensemble(_dev(sims), _dev(meas), _dev(var)) - want) <= 1e-9 * max(1, abs(want))
+        assert abs(eng.loglike_ensemble(_dev(sims), _dev(meas), _dev(var), route='dense') - want) <= 1e-9 * max(1, abs(want))
+        assert abs(eng.loglike_ensemble_diagonal(_dev(sims), _dev(meas), _dev(var))
+                   - OK.ensemble_diagonal_loglike(sims, meas, var)) <= 1e-9 * max(1, abs(want))
+        assert abs(eng.loglike_simple(_dev(sims), _dev(meas), None) - OK.simple_loglike(sims, meas, None)) <= 1e-12 * max(1, abs(want))
+    idx = torch.zeros(0, dtype=torch.int32, device='cuda')
+    assert tuple(eng.gather_columns(_dev(rng.normal(size=(3, 5))), idx).shape) == (3, 0)
+    assert tuple(eng.gather_cov(_dev(np.eye(5)), idx).shape) == (0, 0)
+    with pytest.raises(ValueError):
+        eng.loglike_ensemble(_dev(np.zeros((2, 0))), _dev(np.zeros(0)), _dev(np.zeros(0)))

@@ -186,3 +186,22 @@ def test_invalid_arguments_are_rejected(eng):
     with pytest.raises(ValueError):      # trilinear needs >= 2 vertices per axis
         eng.los_integrate(flat, eng.LosSettings(), dirs, fb['magnetic_field'],
                           torch.zeros(1, 8, dtype=torch.float64).cuda(), None, 1, want=('fd',))
+
+
+def test_edge_cases_empty_and_all_outside(eng):
+    import torch
+    grid = eng.DeviceGrid(BOX, [8, 8, 8])
+    f = eng.field_eval(grid, DESCS, [1, 2], b_stride=16)
+    none = torch.zeros((0, 3), dtype=torch.float64, device='cuda')
+    out = eng.los_integrate(grid, eng.LosSettings(), none, f['magnetic_field'], f['thermal_electron_density'],
+                            f['cosmic_ray_electron_density'], n_real=2)
+    assert all(tuple(t.shape) == (2, 0) for t in out.values())
+    # observer far outside, looking away: every sample is outside the box -> exact zeros
+    away = torch.tensor([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]], dtype=torch.float64, device='cuda')
+    out = eng.los_integrate(grid, eng.LosSettings(observer=(100.0, 100.0, 50.0)), away, f['magnetic_field'],
+                            f['thermal_electron_density'], f['cosmic_ray_electron_density'], n_real=2)
+    assert all(bool((t == 0).all()) for t in out.values())
+    # zero radial steps
+    out = eng.los_integrate(grid, eng.LosSettings(n_steps=0), away, f['magnetic_field'],
+                            f['thermal_electron_density'], None, n_real=2, want=('dm', 'fd'))
+    assert all(bool((t == 0).all()) for t in out.values())
