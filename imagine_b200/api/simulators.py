@@ -26,7 +26,7 @@ from ._bases import Simulator, Simulations
 from .device_observable import DeviceObservable, ShardedDeviceObservable
 from .fields import descriptor_of, device_grid
 from .. import engine
-from ..hotpath import exchange_pixel_shards, gather_rows, shard_bounds
+from ..hotpath import PeerExchange, exchange_pixel_shards, gather_rows, shard_bounds
 
 FIELD_UNITS = {'magnetic_field': u.microgauss, 'thermal_electron_density': u.cm ** -3}
 _NAMES = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
@@ -130,7 +130,7 @@ class B200Simulator(Simulator):
     cre_alpha, cre_beta, cre_theta, cre_E0 : CRE spectrum p = alpha - beta R - theta z at E0 [GeV]
                                         (fields/hamx/cre_analytic.py:19-27)
     rank, world, group : ensemble sharding over torch.distributed ranks (pipeline.py:737-744)
-    exchange : 'auto' | 'alltoall' | 'allgather' -- how the maps reach the likelihood on several ranks
+    exchange : 'auto' | 'peer' | 'alltoall' | 'allgather' -- how the maps reach the likelihood on several ranks
                (hotpath.py); 'alltoall' returns pixel-sharded observables
     """
     SIMULATED_QUANTITIES = ['fd', 'dm', 'sync']
@@ -144,6 +144,7 @@ class B200Simulator(Simulator):
         super().__init__(measurements)
         self.exchange = exchange
         self._send = None
+        self._peer, self._peer_shape = None, None
         self.los_kwargs = dict(observer=tuple(float(u.value_in(v, u.kpc)) for v in observer),
                                dr=float(u.value_in(radial_step, u.kpc)),
                                r_max=float(u.value_in(radial_max, u.kpc)),
@@ -277,13 +278,13 @@ class B200Simulator(Simulator):
 
     # -- pixel-sharded exchange (multi-rank fast path) -------------------------------------------------
     def _can_shard_pixels(self, dev_fields):
-        if self.world <= 1 or self.exchange not in ('auto', 'alltoall'):
+        if self.world <= 1 or self.exchange not in ('auto', 'alltoall', 'peer'):
             return False
         nsides = {int(k[2]) for k in self.observables}
         direct = all(k[0] in ('fd', 'dm') or k[3] in ('I', 'Q', 'U') for k in self.observables)
         per_real = any(t.dim() == 4 or t.shape[0] > 1 for t in dev_fields.values())
         ok = len(nsides) == 1 and direct and per_real and (12 * nsides.pop() ** 2) % self.world == 0
-        if not ok and self.exchange == 'alltoall':
+        if not ok and self.exchange in ('alltoall', 'peer'):
             raise ValueError('exchange="alltoall" needs one Nside divisible over the ranks, only '
                              'fd/dm/I/Q/U observables and at least one stochastic field')
         return ok
@@ -298,12 +299,25 @@ class B200Simulator(Simulator):
         m = 12 * int(self.observables[0][2]) ** 2
         mp = m // self.world
         shape = (self.world, K, n_local, mp)
-        if self._send is None or tuple(self._send.shape) != shape:
-            self._send = torch.empty(shape, dtype=torch.float64, device='cuda')
-        send = self._send
-        views = {key: send[0, k] for k, key in enumerate(self.observables)}
-        self._integrate(dg, dev_fields, n_local, sharded=(views, (mp, K * n_local * mp)))
-        recv = exchange_pixel_shards(send, self.group)
+        if self._peer is None and self.exchange in ('auto', 'peer') and self._peer_shape != shape:
+            self._peer_shape = shape
+            try:                                   # fused NVLink exchange (hotpath.PeerExchange)
+                self._peer = PeerExchange(shape, self.rank, self.group)
+            except Exception:
+                if self.exchange == 'peer':
+                    raise
+        if self._peer is not None and tuple(self._peer.recv.shape) == shape:
+            recv = self._peer.recv
+            views = {key: recv[self.rank, k] for k, key in enumerate(self.observables)}
+            self._integrate(dg, dev_fields, n_local, sharded=(views, (mp, 0, self._peer.peer_delta)))
+            self._peer.barrier()
+        else:
+            if self._send is None or tuple(self._send.shape) != shape:
+                self._send = torch.empty(shape, dtype=torch.float64, device='cuda')
+            send = self._send
+            views = {key: send[0, k] for k, key in enumerate(self.observables)}
+            self._integrate(dg, dev_fields, n_local, sharded=(views, (mp, K * n_local * mp)))
+            recv = exchange_pixel_shards(send, self.group)
         sims = Simulations()
         for k, key in enumerate(self.observables):
             s = self._scale(key)
@@ -344,6 +358,7 @@ class B200Simulator(Simulator):
         state['_dirs'] = {}
         state['_evaluator'] = None
         state['_send'] = None
+        state['_peer'], state['_peer_shape'] = None, None
         state['_row_cache'] = (None, {})
         state['group'] = None
         return state

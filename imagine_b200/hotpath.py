@@ -80,6 +80,30 @@ def exchange_pixel_shards(send, group=None):
     return recv
 
 
+class PeerExchange:
+    """
+    Receive buffer [P(source), K, n_local, m/P] in NVLink symmetric memory, the offsets of every
+    peer's copy relative to mine (what `imb_los_cfg.peer_delta` wants) and the barrier that makes
+    the peer stores of all ranks' LOS kernels visible.  Raises if symmetric memory is unavailable.
+    """
+
+    def __init__(self, shape, rank, group=None, device='cuda'):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.recv = symm_mem.empty(tuple(shape), dtype=torch.float64, device=device)
+        group = group if group is not None else dist.group.WORLD
+        self._handle = symm_mem.rendezvous(self.recv, group.group_name)
+        ptrs = [int(p) for p in self._handle.buffer_ptrs]
+        mine = ptrs[rank]
+        if mine != self.recv.data_ptr() or any((p - mine) % 8 for p in ptrs):
+            raise RuntimeError('unexpected symmetric-memory mapping')
+        self.peer_delta = [(p - mine) // 8 for p in ptrs]
+
+    def barrier(self):
+        self._handle.barrier()
+
+
 class EnsembleEvaluator:
     def __init__(self, box, resolution, nside, los_settings, quantities=('fd', 'dm', 'I', 'Q', 'U'),
                  n_real=1, rank=0, world=1, b_stride=16, group=None, exchange='auto'):
@@ -136,18 +160,9 @@ class EnsembleEvaluator:
 
     def _init_peer_buffers(self, dev):
         """Receive buffer [P(source), K, n_local, m/P] in NVLink symmetric memory + peer offsets."""
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
-        torch = self.torch
         mp = self.m // self.world
-        self.recv = symm_mem.empty((self.world, self.K, self.n_local, mp), dtype=torch.float64, device=dev)
-        group = self.group if self.group is not None else dist.group.WORLD
-        self._symm = symm_mem.rendezvous(self.recv, group.group_name)
-        ptrs = [int(p) for p in self._symm.buffer_ptrs]
-        mine = ptrs[self.rank]
-        assert mine == self.recv.data_ptr()
-        assert all((p - mine) % 8 == 0 for p in ptrs)
-        self.peer_delta = [(p - mine) // 8 for p in ptrs]
+        self._symm = PeerExchange((self.world, self.K, self.n_local, mp), self.rank, self.group, dev)
+        self.recv, self.peer_delta = self._symm.recv, self._symm.peer_delta
         self.send = None
 
     # -- stage 1 + 2 -----------------------------------------------------------------------
