@@ -128,6 +128,8 @@ def check(code):
 def init(device=None):
     """Initialise the library on a CUDA device (default: torch's current device)."""
     global _device
+    if device is None and _device is not None:
+        return _device                      # hot path: already initialised
     import torch
     if not torch.cuda.is_available():
         raise ImbError(IMB_ECUDA, 'imagine_b200 needs a CUDA device (B200, sm_100a); '
@@ -157,7 +159,7 @@ def ptr(t):
 
 def stream_ptr():
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(_device if _device is not None else 0))
 
 
 def make_grid(box, resolution):
