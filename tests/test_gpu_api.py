@@ -285,3 +285,50 @@ def test_four_parameter_lsa_fit_prefers_the_truth(api):
     chain, acc = mod.metropolis(loglike, [5.5, 25.0, 1.0, 22.0], 30, np.array([0.05, 0.3, 0.05, 0.5]),
                                 np.random.default_rng(0))
     assert chain.shape == (30, 4) and 0.0 <= acc <= 1.0
+
+
+def test_config1_basic_pipeline_shapes(api):
+    """
+    BASELINE.json configs[0] = examples/basic_pipeline.py:42-162: grid [100,1,1] on x in [0, 2 pi],
+    10 tabular points, ensemble 48, CosThermalElectronDensity (a = 1, beta = gamma = pi/2) x
+    NaiveGaussianMagneticField, TestSimulator + EnsembleLikelihood -- through the GPU drop-ins,
+    checked against the oracle fed with the GPU-generated realisations.
+    """
+    u = api.units
+    x = np.linspace(0.01, 2. * np.pi - 0.01, 10)
+    np.random.seed(233)
+    signal = (1 + np.cos(x)) * np.random.normal(loc=3., scale=6., size=10)
+    fd = signal + np.random.normal(loc=0., scale=0.1, size=10)              # tutorial_one golden data
+    key = ('test', None, 'tab', None)
+    fd_units = u.microgauss * u.cm ** -3
+    coords = {'x': x * u.kpc, 'y': np.zeros(10) * u.kpc, 'z': np.zeros(10) * u.kpc}
+    meas = api.Measurements()
+    meas.append(name=key, data=fd.reshape(1, 10) * fd_units, cov_data=np.full(10, 0.1 ** 2) * fd_units ** 2,
+                otype='tabular', coords=coords)
+    grid = api.UniformGrid(box=[[0, 2 * np.pi] * u.kpc, [0, 0] * u.kpc, [0, 0] * u.kpc], resolution=[100, 1, 1])
+    N = 48
+    np.random.seed(1)
+    seeds = [int(s) for s in np.random.randint(1, 1431655765, N)]
+    sim, lik = api.B200TestSimulator(meas), api.B200EnsembleLikelihood(meas)
+
+    def fields(a0, b0):
+        return [api.CosThermalElectronDensity(grid, parameters={
+                    'n0': 1 * u.cm ** -3, 'a': 1 * u.rad / u.kpc, 'alpha': 0 * u.rad, 'b': 0 * u.rad / u.kpc,
+                    'beta': np.pi / 2 * u.rad, 'c': 0 * u.rad / u.kpc, 'gamma': np.pi / 2 * u.rad}, ensemble_size=N),
+                api.NaiveGaussianMagneticField(grid, parameters={'a0': a0 * u.microgauss, 'b0': b0 * u.microgauss},
+                                               ensemble_size=N, ensemble_seeds=seeds)]
+
+    fl = fields(3.0, 6.0)
+    sims = sim(fl)
+    assert sims[key].shape == (N, 10)
+    # oracle on the same realisations: fields through the host contract (get_data), sampling + likelihood in NumPy
+    og = OF.Grid([[0, 2 * np.pi], [0, 0], [0, 0]], [100, 1, 1])
+    ne = OF.cos_ne(og, 1, 1, 0, 0, np.pi / 2, 0, np.pi / 2)
+    pts = np.stack([x, np.zeros(10), np.zeros(10)], 1)
+    rows = np.stack([OF.test_simulator_sample(og, fl[1].get_data(i).value, ne, pts, 1) for i in range(N)])
+    assert np.allclose(sims[key].data, rows, rtol=1e-12, atol=0)
+    want = OK.ensemble_loglike(rows, fd, np.full(10, 0.01))
+    got = lik(sims)
+    assert abs(got - want) <= 1e-8 * max(1.0, abs(want))
+    assert lik(sim(fields(3.0, 6.0))) == got                      # same seeds, same answer
+    assert lik(sim(fields(-4.0, 2.5))) != got
