@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) bg_gram_kernel(const __grid_constant__ Ba
   const KeyWs& kw = ws.k[key];
   const int nb = (N + TB - 1) / TB;
   const int bi = blockIdx.y / nb, bj = blockIdx.y % nb;
+  if (bj > bi) return;                 // G and Gw are symmetric: upper tiles are mirrored by the reduce
   const int c0 = blockIdx.x * cols_per_slice;
   const int c_end = min(m, c0 + cols_per_slice);
   const double* __restrict__ X = p.sims[key];
@@ -137,12 +138,14 @@ __global__ void __launch_bounds__(256) bg_gram_kernel(const __grid_constant__ Ba
 
 // dst[e] = sum_s partial[s][e] in slice order; which = 0 -> G, 1 -> P2 (Gw section)
 __global__ void __launch_bounds__(256) bg_reduce_kernel(const __grid_constant__ BatchWs ws, int nn,
-                                                        int slices, int which) {
+                                                        int slices, int which, int N) {
   const KeyWs& kw = ws.k[blockIdx.y];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nn) return;
+  const int i = e / N, j = e % N;
+  const int src = (j / TB > i / TB) ? j * N + i : e;      // upper 64x64 tiles were not computed
   double s = 0.0;
-  for (int k = 0; k < slices; ++k) s += kw.partial[(size_t)k * nn + e];
+  for (int k = 0; k < slices; ++k) s += kw.partial[(size_t)k * nn + src];
   (which == 0 ? kw.G : kw.P2)[e] = s;
 }
 
@@ -344,7 +347,7 @@ static int phase1(const BatchCtx& c, cudaStream_t s) {
   IMB_LAUNCHED();
   bg_gram_kernel<false><<<dim3(c.slices, nb * nb, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, GCOLS, c.L);
   IMB_LAUNCHED();
-  bg_reduce_kernel<<<dim3((c.nn + 255) / 256, c.K), 256, 0, s>>>(c.ws, c.nn, c.slices, 0);
+  bg_reduce_kernel<<<dim3((c.nn + 255) / 256, c.K), 256, 0, s>>>(c.ws, c.nn, c.slices, 0, c.N);
   IMB_LAUNCHED();
   return IMB_OK;
 }
@@ -357,7 +360,7 @@ static int phase2(const BatchCtx& c, double m_total, int estimator, cudaStream_t
   IMB_LAUNCHED();
   bg_gram_kernel<true><<<dim3(c.slices, nb * nb, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, GCOLS, c.L);
   IMB_LAUNCHED();
-  bg_reduce_kernel<<<dim3((c.nn + 255) / 256, c.K), 256, 0, s>>>(c.ws, c.nn, c.slices, 1);
+  bg_reduce_kernel<<<dim3((c.nn + 255) / 256, c.K), 256, 0, s>>>(c.ws, c.nn, c.slices, 1, c.N);
   IMB_LAUNCHED();
   bg_wdot_kernel<<<dim3(c.slices, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, GCOLS, c.L);
   IMB_LAUNCHED();
