@@ -79,6 +79,8 @@ _SIGNATURES = {
                                   C.c_int64, C.c_int, _P, _P, _P]),
     'imb_gram_phase3': (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_double),
                                   C.POINTER(C.c_int32), _P]),
+    'imb_loglike_ensemble_batch_async': (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
+    'imb_gram_phase3_async': (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     'imb_loglike_ensemble_diagonal': (C.c_int, [_P, C.c_int, C.c_int, _P, _P,
                                                 C.POINTER(C.c_double), _P]),
     'imb_loglike_simple': (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int,

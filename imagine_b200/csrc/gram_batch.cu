@@ -387,6 +387,32 @@ static int phase3(const BatchCtx& c, LikeScalars* h_out, cudaStream_t s) {
   return IMB_OK;
 }
 
+// device-side export for the asynchronous entry points: value + a flag (0 ok, else Gram route invalid)
+__global__ void bg_export_kernel(const __grid_constant__ BatchWs ws, int K, double* __restrict__ out,
+                                 int* __restrict__ flag) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const LikeScalars* sc = ws.k[k].sc;
+  out[k] = sc->loglike;
+  if (flag) flag[k] = (sc->nonpos > 0 || sc->info != 0) ? (sc->info != 0 ? sc->info : -1) : 0;
+}
+
+static int finish_async(const BatchCtx& c, double* out_device, int32_t* flag_device, cudaStream_t s) {
+  const int ldt = c.N + 1;
+  const size_t smem = sizeof(double) * (size_t)(c.N + 1) * ldt;
+  const int use_smem = smem <= 200 * 1024;
+  static size_t attr_bytes = 0;
+  if (use_smem && smem > 48 * 1024 && smem > attr_bytes) {
+    IMB_CUDA(cudaFuncSetAttribute(bg_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bytes = smem;
+  }
+  bg_finish_kernel<<<c.K, 256, use_smem ? smem : 0, s>>>(c.ws, c.N, use_smem, ldt);
+  IMB_LAUNCHED();
+  bg_export_kernel<<<1, 32, 0, s>>>(c.ws, c.K, out_device, flag_device);
+  IMB_LAUNCHED();
+  return IMB_OK;
+}
+
 static void unpack(const LikeScalars* h, int K, double* out, int32_t* info, int* fallback) {
   for (int k = 0; k < K; ++k) {
     out[k] = h[k].loglike;
@@ -440,6 +466,34 @@ int imb_loglike_ensemble_batch(int K, const double* const* sims, int N, int m,
   }
   delete[] fallback;
   return rc;
+}
+
+int imb_loglike_ensemble_batch_async(int K, const double* const* sims, int N, int m,
+                                     const double* const* meas, const double* const* var,
+                                     int estimator, double* out_device, int32_t* flag_device,
+                                     void* stream) {
+  IMB_TRY(check_init());
+  cudaStream_t s = (cudaStream_t)stream;
+  if (K < 1 || K > KMAX || !sims || !meas || !var || !out_device || N < 1 || m < 1) return IMB_EINVAL;
+  if (estimator != IMB_EST_EMPIRICAL && estimator != IMB_EST_OAS) return IMB_EINVAL;
+  for (int k = 0; k < K; ++k)
+    if (!sims[k] || !meas[k] || !var[k]) return IMB_EINVAL;
+  const RowLayout L{N, 0, (long long)m};
+  BatchCtx c;
+  IMB_TRY(make_ctx(&c, K, sims, N, m, L, meas, var, nullptr, nullptr));
+  IMB_TRY(phase1(c, s));
+  IMB_TRY(phase2(c, (double)m, estimator, s));
+  return finish_async(c, out_device, flag_device, s);
+}
+
+int imb_gram_phase3_async(int K, int N, int m_local, double* G, double* P2, double* out_device,
+                          int32_t* flag_device, void* stream) {
+  IMB_TRY(check_init());
+  if (K < 1 || K > KMAX || N < 1 || m_local < 1 || !G || !P2 || !out_device) return IMB_EINVAL;
+  const RowLayout L{N, 0, (long long)m_local};
+  BatchCtx c;
+  IMB_TRY(make_ctx(&c, K, nullptr, N, m_local, L, nullptr, nullptr, G, P2));
+  return finish_async(c, out_device, flag_device, (cudaStream_t)stream);
 }
 
 static int sharded_args_ok(int K, const double* const* sims, int N, int m_local, int rpb) {

@@ -326,6 +326,23 @@ def gram_phase3(K, N, m_local, G, P2):
     return [out[k] for k in range(K)]
 
 
+def loglike_ensemble_batch_async(sims, meas, var, out, flags=None, estimator='oas'):
+    """As `loglike_ensemble_batch`, but values go to the device tensor `out` [K] and nothing syncs."""
+    L.init()
+    K = len(sims)
+    N, m = sims[0].shape
+    L.check(L.load().imb_loglike_ensemble_batch_async(K, _ptr_array(sims), N, m, _ptr_array(meas),
+                                                      _ptr_array(var), _EST[estimator], L.ptr(out),
+                                                      L.ptr(flags), L.stream_ptr()))
+
+
+def gram_phase3_async(K, N, m_local, G, P2, out, flags=None):
+    """imb_gram_phase3_async: per-key values into the device tensor `out` [K]; no synchronisation."""
+    L.init()
+    L.check(L.load().imb_gram_phase3_async(K, N, m_local, L.ptr(G), L.ptr(P2), L.ptr(out), L.ptr(flags),
+                                           L.stream_ptr()))
+
+
 def loglike_ensemble_diagonal(sims, meas, var):
     L.init()
     sims, meas, var = _f64(sims, 'sims'), _f64(meas, 'meas').reshape(-1), _f64(var, 'var')

@@ -250,6 +250,50 @@ class EnsembleEvaluator:
             total += v
         return total
 
+    def loglike_async(self, maps, meas, var, out, flags, estimator='oas'):
+        """`loglike` without the host read-back: per-key values into `out` [K] (device)."""
+        qs = self.quantities
+        if self.exchange in ('alltoall', 'peer'):
+            sims = [maps[0, k] for k in range(self.K)]
+            layout = (self.n_local, self.K * self.n_local * self.mp, self.mp)
+            meas_l = [meas[q][self.plo:self.phi] for q in qs]
+            var_l = [var[q][self.plo:self.phi] for q in qs]
+            engine.gram_phase1(sims, self.n_real, self.mp, layout, meas_l, self.G)
+            self._allreduce(self.G)
+            engine.gram_phase2(sims, self.n_real, self.mp, layout, meas_l, var_l, self.m, self.G, self.P2,
+                               estimator=estimator)
+            self._allreduce(self.P2)
+            engine.gram_phase3_async(self.K, self.n_real, self.mp, self.G, self.P2, out, flags)
+        else:
+            engine.loglike_ensemble_batch_async([maps[q] for q in qs], [meas[q] for q in qs],
+                                                [var[q] for q in qs], out, flags, estimator=estimator)
+
+    def evaluate_many(self, points, meas, var, estimator='oas'):
+        """
+        Pipelined evaluation of several parameter points (list of (descs, seeds)): every kernel and
+        collective of every point is enqueued back to back and the host reads all values once --
+        what a vectorised sampler callback (UltraNest `vectorized=True`, emcee walkers, the loop
+        over cubes in pipelines/pipeline.py:976-979) needs.  Returns one log-likelihood per point.
+        """
+        torch = self.torch
+        n = len(points)
+        out = torch.empty((n, self.K), dtype=torch.float64, device=self.dirs.device)
+        flags = torch.zeros((n, self.K), dtype=torch.int32, device=self.dirs.device)
+        for i, (descs, seeds) in enumerate(points):
+            self.simulate(descs, seeds)
+            self.loglike_async(self.gather(), meas, var, out[i], flags[i], estimator)
+        host, bad = out.cpu(), flags.cpu()                      # the one synchronisation
+        if bool(bad.any()):
+            raise np.linalg.LinAlgError('Gram route not applicable (non-positive shrunk diagonal) for '
+                                        'points %s; evaluate them with `evaluate`' % bad.any(1).nonzero().flatten().tolist())
+        totals = []
+        for row in host.tolist():
+            t = 0.0
+            for v in row:
+                t += v
+            totals.append(t)
+        return totals
+
     def _allreduce(self, t):
         if self.world > 1:
             import torch.distributed as dist

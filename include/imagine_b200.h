@@ -244,6 +244,20 @@ int imb_gram_phase2(int K, const double* const* sims, int N, int m_local, int ro
 int imb_gram_phase3(int K, int N, int m_local, double* G, double* P2, double* out_loglike,
                     int32_t* out_info, void* stream);
 
+/*
+ * Asynchronous variants (K <= 16): the per-key values land in DEVICE memory (out_device [K]) with
+ * flag_device [K] (may be NULL; 0 = ok, non-zero = Gram route not applicable for that key) and the
+ * call does not synchronise.  Lets a caller pipeline many parameter points -- UltraNest
+ * `vectorized`, emcee walkers, the MPI loop over cubes (pipelines/pipeline.py:976-979) -- and read
+ * all values back once.  No dense-route fallback here: check the flags.
+ */
+int imb_loglike_ensemble_batch_async(int K, const double* const* sims, int N, int m,
+                                     const double* const* meas, const double* const* var,
+                                     int estimator, double* out_device, int32_t* flag_device,
+                                     void* stream);
+int imb_gram_phase3_async(int K, int N, int m_local, double* G, double* P2, double* out_device,
+                          int32_t* flag_device, void* stream);
+
 /* EnsembleLikelihoodDiagonal.call (likelihoods/ensemble_likelihood.py:137-173);
  * var [m] = diagonal of the measurement covariance.  Synchronises. */
 int imb_loglike_ensemble_diagonal(const double* sims, int N, int m, const double* meas,

@@ -120,3 +120,28 @@ def test_c2_dense_route_equals_gram_route_at_nside32():
     # same number from the m x m factorisation and from the N x N Gram matrix (SURVEY finding 5)
     assert abs(d - g) <= 1e-8 * max(1.0, abs(g) * 1e-5), (d, g, dt)
     print('dense route m=12288: %.3f s' % dt)
+
+
+def test_pipelined_multi_point_evaluation_matches_sequential():
+    """several parameter points enqueued back to back, one read-back == one by one."""
+    import torch
+    from imagine_b200 import engine, _lib
+    from imagine_b200.hotpath import EnsembleEvaluator
+    _lib.init(0)
+    ev = EnsembleEvaluator(BOX, [32] * 3, 16, engine.LosSettings(**LOS_KW), n_real=8)
+    seeds = np.arange(1, 9, dtype=np.uint64)
+    m = 12 * 16 ** 2
+    gen = torch.Generator().manual_seed(0)
+    meas = {q: (torch.randn(m, dtype=torch.float64, generator=gen) * s).cuda()
+            for q, s in zip(ev.quantities, (30.0, 100.0, 1e-4, 1e-4, 1e-4))}
+    var = {q: torch.full((m,), sc ** 2, dtype=torch.float64, device='cuda')
+           for q, sc in zip(ev.quantities, (3.0, 10.0, 1e-5, 1e-5, 1e-5))}
+    points = []
+    for by, sigma in [(1.0, 2.0), (0.5, 1.0), (2.0, 3.0), (1.0, 2.0)]:
+        descs = [(OF.EXP_NE, [0.01, 3.0, 0.5], 0), (OF.CONST_B, [0.0, by, 0.0], 1), (OF.GAUSS_B, [0.0, sigma], 2),
+                 (OF.CRE_ANALYTIC, [0.0217, 5.0, 1.0, 8.3], 3)]
+        points.append((descs, seeds))
+    one_by_one = [ev.evaluate(d, s, meas, var) for d, s in points]
+    batched = ev.evaluate_many(points, meas, var)
+    assert batched == one_by_one
+    assert batched[0] == batched[3] and batched[0] != batched[1]
