@@ -228,10 +228,12 @@ __global__ void __launch_bounds__(256) bg_pack2_kernel(const __grid_constant__ B
   const KeyWs& kw = ws.k[blockIdx.x];
   const int tid = threadIdx.x, nt = blockDim.x;
   double* tail = kw.P2 + (size_t)N * N;
-  for (int r = tid; r < N; r += nt) {
+  // y[r]: warp per row, lanes stride over the slices, fixed-order shuffle tree
+  for (int r = tid >> 5; r < N; r += nt >> 5) {
     double s = 0.0;
-    for (int k = 0; k < slices; ++k) s += kw.ypart[(size_t)k * N + r];
-    tail[r] = s;
+    for (int k = tid & 31; k < slices; k += 32) s += kw.ypart[(size_t)k * N + r];
+    s = warp_sum(s);
+    if ((tid & 31) == 0) tail[r] = s;
   }
   double a = 0, b = 0, c = 0, d = 0;                 // fixed order: thread t takes parts t, t+nt, ...
   for (int k = tid; k < dparts; k += nt) {
