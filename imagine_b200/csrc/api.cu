@@ -41,6 +41,21 @@ int ensure_workspace(size_t bytes) {
   return IMB_OK;
 }
 
+int ensure_buffer(void** buf, size_t* cap, size_t bytes) {
+  if (bytes <= *cap) return IMB_OK;
+  IMB_CUDA(cudaDeviceSynchronize());
+  if (*buf) {
+    IMB_CUDA(cudaFree(*buf));
+    *buf = nullptr;
+    *cap = 0;
+  }
+  const size_t want = align_up(bytes, (size_t)1 << 16);
+  cudaError_t e = cudaMalloc(buf, want);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaMalloc(buffer)");
+  *cap = want;
+  return IMB_OK;
+}
+
 }  // namespace imb
 
 using imb::state;
@@ -74,6 +89,10 @@ int imb_finalize(void) {
   if (!s.initialised) return IMB_OK;
   cudaDeviceSynchronize();
   if (s.ws) cudaFree(s.ws);
+  if (s.seeds) cudaFree(s.seeds);
+  if (s.aux) cudaFree(s.aux);
+  s.seeds = s.aux = nullptr;
+  s.seeds_bytes = s.aux_bytes = 0;
   if (s.pinned) cudaFreeHost(s.pinned);
   s.ws = nullptr;
   s.ws_bytes = 0;

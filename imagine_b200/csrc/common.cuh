@@ -14,6 +14,13 @@ struct State {
   int sm_count = 148;
   void* ws = nullptr;          // scratch workspace (device)
   size_t ws_bytes = 0;
+  // dedicated small buffers, so that field evaluation and LOS integration may run on different
+  // streams without touching the likelihood scratch: seed slots (rotating) and packed (n_e, CRE)
+  void* seeds = nullptr;
+  size_t seeds_bytes = 0;
+  unsigned seeds_slot = 0;
+  void* aux = nullptr;
+  size_t aux_bytes = 0;
   void* pinned = nullptr;      // small pinned host buffer for scalar read-back
   size_t pinned_bytes = 0;
   long long launches = 0;
@@ -22,6 +29,7 @@ struct State {
 State& state();
 int set_cuda_error(cudaError_t e, const char* where);
 int ensure_workspace(size_t bytes);   // grows state().ws; returns IMB_* code
+int ensure_buffer(void** buf, size_t* cap, size_t bytes);   // same for a dedicated buffer
 int check_init();
 
 #define IMB_CUDA(call)                                                     \

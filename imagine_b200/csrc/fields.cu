@@ -409,8 +409,13 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
   // seeds -> device scratch (pageable H2D is staged before the call returns)
   if (n_seed_rows < 0) return IMB_EINVAL;
   const size_t n_seeds = (size_t)(n_seed_rows > 0 ? n_seed_rows : 1) * (size_t)n_real;
-  IMB_TRY(ensure_workspace(sizeof(unsigned long long) * n_seeds + 256));
-  unsigned long long* d_seeds = static_cast<unsigned long long*>(state().ws);
+  // four rotating slots: a later call (possibly on another stream) never overwrites the seeds a
+  // kernel still in flight is reading
+  const size_t slot_bytes = align_up(sizeof(unsigned long long) * n_seeds, 256);
+  IMB_TRY(ensure_buffer(&state().seeds, &state().seeds_bytes, 4 * slot_bytes));
+  unsigned long long* d_seeds = reinterpret_cast<unsigned long long*>(
+      static_cast<char*>(state().seeds) +
+      (state().seeds_slot++ % 4) * (state().seeds_bytes / 4 / 256 * 256));   // capacity-based stride
   bool any_stochastic = false;
   for (int f = 0; f < nfields; ++f) {
     if (!is_stochastic(fields[f].kind)) continue;

@@ -462,8 +462,8 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
   }
   if (b_stride == 16 && has_ne && has_cre && rows_ne == 1 && rows_cre == 1) {
     // pack the two shared scalar grids into (n_e, CRE) pairs: one 128-bit gather per vertex
-    IMB_TRY(ensure_workspace(sizeof(double) * 2 * (size_t)a.g.ncell + 256));
-    double* packed = static_cast<double*>(state().ws);
+    IMB_TRY(ensure_buffer(&state().aux, &state().aux_bytes, sizeof(double) * 2 * (size_t)a.g.ncell));
+    double* packed = static_cast<double*>(state().aux);
     pack_pairs_kernel<<<grid_blocks(a.g.ncell, 256, 8), 256, 0, (cudaStream_t)stream>>>(ne, cre, a.g.ncell, packed);
     IMB_LAUNCHED();
     a.necre = packed;
