@@ -110,15 +110,15 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def cpu_reference(workload, budget='baseline'):
-    """Bounded CPU sample sized for roughly 10-30 s of work on the box's host cores."""
+def cpu_reference(workload, budget_s=15.0):
+    """Bounded CPU sample sized for roughly `budget_s` seconds of work on the box's host cores."""
     from oracle import cpu_path
     w = WORKLOADS[workload]
     cores = cpu_path.host_cores()
     n_s = max(1, min(cores, w['n_real']))
     m = 12 * w['nside'] ** 2
-    # ~1 ms of NumPy work per (pixel, realisation) for all five observables
-    target = (12000 if budget == 'baseline' else 20000) * cores
+    # ~1 ms of NumPy work per (pixel, realisation) and core for all five observables
+    target = max(64 * cores, 800.0 * cores * budget_s)
     frac = min(1.0, target / float(n_s * m))
     res = cpu_path.time_sample(BOX, [w['G']] * 3, w['nside'], field_descs(w['quantities']),
                                ensemble_seeds(w['n_real']), LOS_KW, w['n_real'], n_real_sample=n_s,
@@ -133,14 +133,14 @@ def run_reference(args):
         return
     w = WORKLOADS[args.workload]
     times, last = [], None
+    # every step is a bounded sample; the whole --steps/--warmup run is sized for ~3 minutes
+    budget_s = min(20.0, max(1.0, 150.0 / max(1, args.warmup + args.steps)))
+    t_run = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        last = cpu_reference(args.workload, budget='reference')
-        wall = time.perf_counter() - t0
+        last = cpu_reference(args.workload, budget_s=budget_s)
         if i >= args.warmup:
             times.append(last['seconds_per_eval'])
-        if wall * (args.warmup + args.steps - i - 1) > 240:      # keep the whole run bounded
-            times = times or [last['seconds_per_eval']]
+        if time.perf_counter() - t_run > 400 and times:         # hard stop, never hang the driver
             break
     sec = float(np.mean(times))
     value = 1.0 / sec
@@ -392,7 +392,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             try:
-                res = cpu_reference(args.workload, budget='baseline')
+                res = cpu_reference(args.workload, budget_s=15.0)
                 line['cpu_baseline'] = {'value': 1.0 / res['seconds_per_eval'], 'unit': 'evals/s',
                                         'cores': res['cores'], 'kind': 'port', 'sample': res['sample'],
                                         'stages_s': res['stages']}

@@ -27,7 +27,7 @@ struct PixConst {          // per warp, in shared memory
 
 template <bool HAS_NE, bool HAS_CRE, bool VAR_P, bool P3, int NG, int MINB>
 __global__ void __launch_bounds__(256, MINB) los_il4s_kernel(const __grid_constant__ LosArgs a) {
-  extern __shared__ double s_acc[];                     // [NG*5][256]
+  extern __shared__ double s_acc[];                     // [NG*nslot][256]
   __shared__ PixConst s_pix[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = lane >> 2, r4 = lane & 3;
@@ -66,7 +66,9 @@ __global__ void __launch_bounds__(256, MINB) los_il4s_kernel(const __grid_consta
     pc.j_lo = j_lo; pc.j_hi = j_hi;
   }
 #pragma unroll
-  for (int q = 0; q < NG * 5; ++q) s_acc[q * 256 + tid] = 0.0;
+  // slots per group: carry, I, Q, U (+ DM only when n_e differs per realisation)
+  const int nslot = (HAS_NE && a.ne_row != 0) ? 5 : 4;
+  for (int q = 0; q < NG * nslot; ++q) s_acc[q * 256 + tid] = 0.0;
   __syncwarp();
 
   const int j_hi = pc.j_hi;
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(256, MINB) los_il4s_kernel(const __grid_consta
         x10 = lerp(x10, x01, c.ty); y10 = lerp(y10, y01, c.ty); z10 = lerp(z10, z01, c.ty);
         bx = lerp(x00, x10, c.tx); by = lerp(y00, y10, c.tx); bz = lerp(z00, z10, c.tx);
       }
-      double* acc = s_acc + (size_t)(t * 5) * 256 + tid;     // [0] carry, [1] DM, [2] I, [3] Q, [4] U
+      double* acc = s_acc + (size_t)(t * nslot) * 256 + tid;  // [0] carry, [1] I, [2] Q, [3] U, [4] DM
       double phi = 0.0;
       if (HAS_NE) {
         if (!ne_shared) ne_s = live ? interp_scalar(a.ne + a.ne_row * rr, c) : 0.0;
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(256, MINB) los_il4s_kernel(const __grid_consta
         const double carry = acc[0];
         phi = (carry + x) - 0.5 * f;
         acc[0] = carry + __shfl_sync(0xffffffffu, x, 28 + r4);
-        if (!ne_shared) acc[256] += ne_s * a.dl_pc;
+        if (!ne_shared) acc[1024] += ne_s * a.dl_pc;
       }
       if (HAS_CRE) {
         if (!cre_shared) cre_s = live ? interp_scalar(a.cre + a.cre_row * rr, c) : 0.0;
@@ -174,15 +176,15 @@ __global__ void __launch_bounds__(256, MINB) los_il4s_kernel(const __grid_consta
             qc = gq * (bn2 - be2);
             uc = gq * (2.0 * bn * be);
           }
-          acc[512] += em;
+          acc[256] += em;
           if (HAS_NE) {
             double sa, ca;
             sincos(2.0 * phi * a.lam2, &sa, &ca);
-            acc[768] += qc * ca - uc * sa;
-            acc[1024] += qc * sa + uc * ca;
+            acc[512] += qc * ca - uc * sa;
+            acc[768] += qc * sa + uc * ca;
           } else {
-            acc[768] += qc;
-            acc[1024] += uc;
+            acc[512] += qc;
+            acc[768] += uc;
           }
         }
       }
@@ -194,8 +196,8 @@ __global__ void __launch_bounds__(256, MINB) los_il4s_kernel(const __grid_consta
     const int g = g0 + t;
     if (g >= n_groups) break;
     const int rr = g * 4 + r4;
-    const double* acc = s_acc + (size_t)(t * 5) * 256 + tid;
-    double dm = dm_shared ? dm_total : acc[256], I = acc[512], Q = acc[768], U = acc[1024];
+    const double* acc = s_acc + (size_t)(t * nslot) * 256 + tid;
+    double dm = dm_shared ? dm_total : acc[1024], I = acc[256], Q = acc[512], U = acc[768];
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) {
       if (HAS_NE) dm += __shfl_xor_sync(0xffffffffu, dm, o);
@@ -223,10 +225,11 @@ __global__ void __launch_bounds__(256, MINB) los_il4s_kernel(const __grid_consta
 template <bool HAS_NE, bool HAS_CRE, bool VAR_P, bool P3, int NG, int MINB>
 static int launch_one(const LosArgs& a, dim3 grid, cudaStream_t s) {
   auto kern = los_il4s_kernel<HAS_NE, HAS_CRE, VAR_P, P3, NG, MINB>;
-  const size_t smem = sizeof(double) * NG * 5 * 256;
+  const size_t smem = sizeof(double) * NG * ((HAS_NE && a.ne_row != 0) ? 5 : 4) * 256;
+  const size_t smem_max = sizeof(double) * NG * 5 * 256;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(los_il4s_kernel)");
     configured = true;
   }
