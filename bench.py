@@ -373,8 +373,8 @@ def main():
             'roofline': {'kernel': 'los_il4s_kernel', 'bound': 'hbm', 'achieved': los_gbs, 'peak': peak,
                          'unit': 'GB/s', 'frac': los_gbs / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full,
-                         # profiles/r01_ncu_full_v3_los_il4s.csv (c3, 1 GPU only)
-                         'traffic': 3919345136 if (args.workload == 'c3' and world == 1) else None,
+                         # profiles/r01_ncu_full_final.csv (c3, 1 GPU only)
+                         'traffic': 3914488000 if (args.workload == 'c3' and world == 1) else None,
                          'limiter': 'L1 data-pipe wavefronts of the trilinear gathers (86 % of peak); '
                                     'the padded B grid leaves HBM once (DRAM 8 % busy)',
                          'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)',
