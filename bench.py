@@ -178,6 +178,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--points', type=int, default=8, help='parameter points per pipelined flush (extra key)')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'peer', 'alltoall', 'allgather'])
+    ap.add_argument('--b-stride', default='auto', help="field layout: 'auto' | 16 | 48 | 96 (A/B runs)")
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -207,8 +208,9 @@ def main():
     descs = field_descs(quantities)
     seeds = ensemble_seeds(N)
     settings = engine.LosSettings(**LOS_KW)
+    b_stride = args.b_stride if args.b_stride == 'auto' else int(args.b_stride)
     ev = EnsembleEvaluator(BOX, [G] * 3, nside, settings, quantities, n_real=N, rank=rank, world=world,
-                           exchange=args.exchange)
+                           exchange=args.exchange, b_stride=b_stride)
 
     # ---- synthetic measurements: one realisation from an independent seed + 1% noise --------
     mock = EnsembleEvaluator(BOX, [G] * 3, nside, settings, quantities, n_real=1, exchange='allgather')
@@ -300,7 +302,7 @@ def main():
                         cov_data=var_h[q].numpy() * unit_of[q] ** 2, otype='HEALPix')
     api_sim = api.B200Simulator(api_meas, observer=LOS_KW['observer'], radial_step=LOS_KW['dr'],
                                 radial_max=LOS_KW['r_max'], cre_alpha=LOS_KW['alpha'], cre_E0=LOS_KW['e0_gev'],
-                                rank=rank, world=world)
+                                rank=rank, world=world, b_stride=b_stride)
     api_lik = api.B200EnsembleLikelihood(api_meas)
     seed_list = [int(v) for v in seeds]
     h2d = sum(meas_h[q].numel() * 8 + var_h[q].numel() * 8 for q in quantities) + len(seed_list) * 8
@@ -370,7 +372,7 @@ def main():
                     'ms_per_step': max(e2e_ms, e2e_wall_ms) / args.steps},
             'gpu_launches': int(launches),
             'clocks': clocks,
-            'roofline': {'kernel': 'los_il4s_kernel', 'bound': 'hbm', 'achieved': los_gbs, 'peak': peak,
+            'roofline': {'kernel': 'los_il4s_kernel' if ev.b_stride == 16 else 'los_rl_kernel', 'bound': 'hbm', 'achieved': los_gbs, 'peak': peak,
                          'unit': 'GB/s', 'frac': los_gbs / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full,
                          # profiles/r01_ncu_full_final.csv (c3, 1 GPU only)

@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libimagine_b200.so')
-SOURCES = ['api.cu', 'fields.cu', 'los.cu', 'los_il4.cu', 'likelihood.cu', 'gram_batch.cu', 'dense.cu']
+SOURCES = ['api.cu', 'fields.cu', 'los.cu', 'los_il4.cu', 'los_rl.cu', 'likelihood.cu', 'gram_batch.cu', 'dense.cu']
 HEADERS = ['common.cuh', 'linalg.cuh', 'los.cuh', os.path.join('..', '..', 'include', 'imagine_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared', '-cudart', 'static']

@@ -67,7 +67,7 @@ class _DeviceFieldEvaluator:
 
     def __init__(self, b_stride):
         self.b_stride = b_stride
-        self.effective_b_stride = 4 if b_stride == 16 else b_stride
+        self.effective_b_stride = 4
         self._bufs = {}
 
     def evaluate(self, fields, grid, lo, hi):
@@ -86,8 +86,8 @@ class _DeviceFieldEvaluator:
                 row = len(seed_rows) - 1
             descs.append((d[0], d[1], d[2], row))
         seeds = np.stack(seed_rows) if seed_rows else np.zeros((1, n_local), dtype=np.uint64)
-        b_stride = self.b_stride
-        if b_stride == 16 and any(f.type == 'magnetic_field' for f in foreign):
+        b_stride = engine.pick_b_stride(n_local) if self.b_stride == 'auto' else self.b_stride
+        if b_stride in engine.INTERLEAVED_STRIDES and any(f.type == 'magnetic_field' for f in foreign):
             b_stride = 4              # host arrays are summed in the row-major padded layout
         out = {}
         if descs:
@@ -100,7 +100,7 @@ class _DeviceFieldEvaluator:
                     self._bufs[name] = buf
                 out[name] = buf
             out = engine.field_eval(dg, descs, seeds, n_real=n_local, b_stride=b_stride, out=out)
-        self.effective_b_stride = b_stride if b_stride != 16 else 4
+        self.effective_b_stride = b_stride if b_stride not in engine.INTERLEAVED_STRIDES else 4
         # foreign plugins: host get_data -> upload -> device sum (simulator.py:166-178 semantics)
         for f in foreign:
             unit = FIELD_UNITS.get(f.type, f.units)
@@ -139,7 +139,7 @@ class B200Simulator(Simulator):
     ALLOWED_GRID_TYPES = ['cartesian']
 
     def __init__(self, measurements, observer=(-8.3, 0.0, 0.006), radial_step=0.1, radial_max=30.0,
-                 cre_alpha=3.0, cre_beta=0.0, cre_theta=0.0, cre_E0=20.6, b_stride=16,
+                 cre_alpha=3.0, cre_beta=0.0, cre_theta=0.0, cre_E0=20.6, b_stride='auto',
                  rank=0, world=1, group=None, exchange='auto'):
         super().__init__(measurements)
         self.exchange = exchange
@@ -150,7 +150,7 @@ class B200Simulator(Simulator):
                                r_max=float(u.value_in(radial_max, u.kpc)),
                                alpha=float(cre_alpha), beta=float(cre_beta), theta=float(cre_theta),
                                e0_gev=float(cre_E0))
-        self.b_stride = int(b_stride)
+        self.b_stride = b_stride if b_stride == 'auto' else int(b_stride)
         self._evaluator = None
         self.rank, self.world, self.group = int(rank), int(world), group
         self._dirs = {}

@@ -169,6 +169,52 @@ __global__ void __launch_bounds__(256) field_b_il4_kernel(const __grid_constant_
   }
 }
 
+// ---- magnetic field, wide realisation-interleaved layout (b_stride 3*RL, RL = 32 | 16) ---------
+// out[group][cell][component][RL], group = r / RL: what the lane-per-realisation LOS kernel
+// (los_rl.cu) reads with one coalesced 64-bit load per corner component.  Thread = (pair of cells,
+// realisation), realisation fastest, so each of the six stores of a warp is RL*8 contiguous bytes.
+template <int RL>
+__global__ void __launch_bounds__(256) field_b_rl_kernel(const __grid_constant__ FieldArgs a,
+                                                         double* __restrict__ out) {
+  const unsigned int npair_rl = (unsigned int)((a.g.ncell + 1) >> 1) * (unsigned int)RL;
+  const int g = blockIdx.y;
+  for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < npair_rl; w += gridDim.x * blockDim.x) {
+    const int rl = (int)(w % RL);
+    const unsigned int q = w / RL;
+    const int r = g * RL + rl;
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (r < a.rows) {
+      bool first = true;
+      for (int f = 0; f < a.nfields; ++f) {
+        double t[6];
+        if (a.kind[f] == IMB_FIELD_CONST_B) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) t[k] = a.p[f][k % 3];
+        } else if (a.kind[f] == IMB_FIELD_LSA_B) {
+          lsa_pair(a.g, a.p[f], 2ll * q, (2ll * q + 1) < a.g.ncell, t);
+        } else {
+          const unsigned long long seed = a.seeds[(size_t)a.seed_row[f] * a.n_real + r];
+          const double mu = a.p[f][0], sigma = a.p[f][1];
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            double z0, z1;
+            philox_normal_pair(seed, a.stream[f], 3ull * q + b, z0, z1);
+            t[2 * b] = __dadd_rn(__dmul_rn(z0, sigma), mu);
+            t[2 * b + 1] = __dadd_rn(__dmul_rn(z1, sigma), mu);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] = first ? t[k] : __dadd_rn(v[k], t[k]);
+        first = false;
+      }
+    }
+    const long long c0 = 2ll * q;
+    double* o = out + ((long long)g * a.g.ncell + c0) * (3 * RL) + rl;
+    o[0] = v[0]; o[RL] = v[1]; o[2 * RL] = v[2];
+    if (c0 + 1 < a.g.ncell) { o[3 * RL] = v[3]; o[4 * RL] = v[4]; o[5 * RL] = v[5]; }
+  }
+}
+
 // ---- scalar fields (thermal electrons, cosmic-ray electrons): [rows, ncell] -----------
 __device__ __forceinline__ double scalar_model(const FieldArgs& a, int f, double x, double y,
                                                double z) {
@@ -402,7 +448,8 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
   DevGrid g;
   IMB_TRY(make_dev_grid(grid, &g));
   if (!fields || nfields < 0 || n_real < 1) return IMB_EINVAL;
-  if (out_B && b_stride != 3 && b_stride != 4 && b_stride != 16) return IMB_EINVAL;
+  if (out_B && b_stride != 3 && b_stride != 4 && b_stride != 16 && b_stride != 48 && b_stride != 96)
+    return IMB_EINVAL;
   for (int f = 0; f < nfields; ++f)
     if (field_type(fields[f].kind) < 0) return IMB_EINVAL;
 
@@ -464,6 +511,16 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
         int bx = grid_blocks(work4, 256, 8) / n_groups;
         if (bx < 1) bx = 1;
         field_b_il4_kernel<<<dim3(bx, n_groups), 256, 0, stream>>>(a, outs[type]);
+      } else if (b_stride == 48 || b_stride == 96) {
+        // wide interleave: [ceil(rows/RL), ncell, 3, RL]
+        const int rl = b_stride / 3;
+        if (need != n_real || addr % 32 != 0) return IMB_EINVAL;
+        if ((g.ncell + 1) / 2 * rl >= (1ll << 32)) return IMB_EUNSUPPORTED;   // 32-bit work index
+        const int n_groups = (need + rl - 1) / rl;
+        int bx = grid_blocks(((g.ncell + 1) / 2) * rl, 256, 8) / n_groups;
+        if (bx < 1) bx = 1;
+        if (rl == 32) field_b_rl_kernel<32><<<dim3(bx, n_groups), 256, 0, stream>>>(a, outs[type]);
+        else field_b_rl_kernel<16><<<dim3(bx, n_groups), 256, 0, stream>>>(a, outs[type]);
       } else if (b_stride == 3) {
         const bool vec = (addr % 16 == 0) && (need == 1 || row_elems % 2 == 0);
         if (vec) field_b_kernel<3, true><<<blocks, 256, 0, stream>>>(a, outs[type]);

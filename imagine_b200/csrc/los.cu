@@ -16,6 +16,7 @@ namespace imb {
 
 int make_dev_grid(const imb_grid* grid, DevGrid* g);
 int launch_los_il4s(const LosArgs& a, bool has_ne, bool has_cre, bool var_p, cudaStream_t s);
+int launch_los_rl(const LosArgs& a, int rl, bool has_ne, bool has_cre, bool var_p, cudaStream_t s);
 
 template <bool HAS_NE, bool HAS_CRE, bool VAR_P, int RT, int BS>
 __global__ void __launch_bounds__(256) los_kernel(const __grid_constant__ LosArgs a) {
@@ -400,9 +401,10 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
   IMB_TRY(make_dev_grid(grid, &a.g));
   if (m == 0 && cfg && n_real >= 1) return IMB_OK;            // nothing to integrate
   if (!cfg || !dirs || !B || m < 0 || n_real < 1) return IMB_EINVAL;
-  if (b_stride != 3 && b_stride != 4 && b_stride != 16) return IMB_EINVAL;
+  if (b_stride != 3 && b_stride != 4 && b_stride != 16 && b_stride != 48 && b_stride != 96)
+    return IMB_EINVAL;
   if (b_stride >= 4 && (reinterpret_cast<uintptr_t>(B) % 32 != 0)) return IMB_EINVAL;
-  if (b_stride == 16 && rows_B != n_real) return IMB_EINVAL;   // interleaved layout is per realisation
+  if (b_stride >= 16 && rows_B != n_real) return IMB_EINVAL;   // interleaved layouts are per realisation
   for (int k = 0; k < 3; ++k)
     if (grid->n[k] < 2 || !(grid->hi[k] > grid->lo[k])) return IMB_EINVAL;  // trilinear needs a cell
   if (cfg->n_steps < 0 || !(cfg->dr > 0.0)) return IMB_EINVAL;
@@ -460,7 +462,7 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
     a.n_peers = cfg->n_peers;
     for (int d = 0; d < cfg->n_peers; ++d) a.peer_delta[d] = cfg->peer_delta[d];
   }
-  if (b_stride == 16 && has_ne && has_cre && rows_ne == 1 && rows_cre == 1) {
+  if (b_stride >= 16 && has_ne && has_cre && rows_ne == 1 && rows_cre == 1) {
     // pack the two shared scalar grids into (n_e, CRE) pairs: one 128-bit gather per vertex
     IMB_TRY(ensure_buffer(&state().aux, &state().aux_bytes, sizeof(double) * 2 * (size_t)a.g.ncell));
     double* packed = static_cast<double*>(state().aux);
@@ -480,6 +482,11 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
     rt = n_real >= 4 ? 4 : (n_real >= 2 ? 2 : 1);
   }
   cudaStream_t s = (cudaStream_t)stream;
+  if (b_stride == 48 || b_stride == 96) {     // lane = realisation (los_rl.cu)
+    IMB_TRY(launch_los_rl(a, b_stride / 3, has_ne, has_cre, var_p, s));
+    IMB_LAUNCHED();
+    return IMB_OK;
+  }
   if (b_stride == 16 && !getenv("IMB_LOS_REGISTER_ACC")) {
     IMB_TRY(launch_los_il4s(a, has_ne, has_cre, var_p, s));
     IMB_LAUNCHED();

@@ -80,26 +80,56 @@ def field_rows(descs, n_real):
 FIELD_NAMES = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
 
 
+INTERLEAVED_STRIDES = (16, 48, 96)
+
+
+def pick_b_stride(n_real):
+    """Widest realisation interleave a block of `n_real` realisations fills without padding:
+    96 = [group][cell][3][32] and 48 = [group][cell][3][16] (lane-per-realisation LOS kernel,
+    los_rl.cu), else 16 = [group][cell][4][4] (los_il4.cu)."""
+    if n_real % 32 == 0:
+        return 96
+    if n_real % 16 == 0:
+        return 48
+    return 16
+
+
+def b_shape(rows, ncell, b_stride):
+    """Shape of the magnetic-field buffer for a layout code."""
+    if b_stride == 16:
+        return ((rows + 3) // 4, ncell, 4, 4)           # [group][cell][realisation % 4][x,y,z,0]
+    if b_stride in (48, 96):
+        rl = b_stride // 3
+        return ((rows + rl - 1) // rl, ncell, 3, rl)    # [group][cell][x|y|z][realisation % RL]
+    return (rows, ncell, b_stride)
+
+
+def b_stride_of(B):
+    """Layout code of a magnetic-field buffer (inverse of `b_shape`)."""
+    if B.dim() == 4:
+        return 16 if tuple(B.shape[-2:]) == (4, 4) else 3 * int(B.shape[-1])
+    return int(B.shape[-1])
+
+
 def field_shapes(grid, descs, n_real, b_stride=4):
     """Buffer shapes `field_eval` will use/expect: {name: shape}, plus the effective b_stride."""
     rows = field_rows(descs, n_real)
-    if b_stride == 16 and rows[0] != n_real:
+    if b_stride == 'auto':
+        b_stride = pick_b_stride(n_real)
+    if b_stride in INTERLEAVED_STRIDES and rows[0] != n_real:
         b_stride = 4
     shapes = {}
     for t, name in enumerate(FIELD_NAMES):
         if rows[t] == 0:
             continue
-        if t == 0 and b_stride == 16:
-            shapes[name] = ((rows[0] + 3) // 4, grid.ncell, 4, 4)
-        else:
-            shapes[name] = (rows[t], grid.ncell, b_stride) if t == 0 else (rows[t], grid.ncell)
+        shapes[name] = b_shape(rows[0], grid.ncell, b_stride) if t == 0 else (rows[t], grid.ncell)
     return shapes, b_stride
 
 
 def field_eval(grid, descs, seeds, n_real=None, b_stride=4, out=None):
     """
     Evaluate and sum all fields (imb_field_eval).  Returns dict with any of
-    'magnetic_field' [rows, ncell, b_stride], 'thermal_electron_density' [rows, ncell],
+    'magnetic_field' [rows, ncell, b_stride] (or an interleaved `b_shape`), 'thermal_electron_density' [rows, ncell],
     'cosmic_ray_electron_density' [rows, ncell]; rows is n_real when a stochastic field of the
     type is present and 1 otherwise.  `descs` entries are (kind, params, philox_stream[, seed_row]);
     `seeds` is [n_real] or [n_seed_rows, n_real].
@@ -115,15 +145,14 @@ def field_eval(grid, descs, seeds, n_real=None, b_stride=4, out=None):
     rows = field_rows(descs, n_real)
     names = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
     bufs = {}
-    if b_stride == 16 and rows[0] != n_real:
+    if b_stride == 'auto':
+        b_stride = pick_b_stride(n_real)
+    if b_stride in INTERLEAVED_STRIDES and rows[0] != n_real:
         b_stride = 4          # interleaving realisations only makes sense for a stochastic B
     for t, name in enumerate(names):
         if rows[t] == 0:
             continue
-        if t == 0 and b_stride == 16:
-            shape = ((rows[0] + 3) // 4, grid.ncell, 4, 4)      # [group][cell][realisation%4][x,y,z,0]
-        else:
-            shape = (rows[t], grid.ncell, b_stride) if t == 0 else (rows[t], grid.ncell)
+        shape = b_shape(rows[0], grid.ncell, b_stride) if t == 0 else (rows[t], grid.ncell)
         if out is not None and name in out:
             buf = out[name]
             if tuple(buf.shape) != shape:
@@ -185,10 +214,10 @@ def los_integrate(grid, settings, dirs, B, ne=None, cre=None, n_real=1,
             else:
                 res[k] = torch.empty((n_real, m), dtype=torch.float64, device=B.device)
     cfg = settings.c_struct(*(out_layout or (0, 0)))
-    interleaved = B.dim() == 4                      # [group][cell][4][4] realisation-interleaved layout
+    interleaved = B.dim() == 4                      # realisation-interleaved layouts (b_shape)
     L.check(L.load().imb_los_integrate(
         C.byref(grid.c), C.byref(cfg), L.ptr(dirs), m, L.ptr(B),
-        n_real if interleaved else B.shape[0], 16 if interleaved else B.shape[-1],
+        n_real if interleaved else B.shape[0], b_stride_of(B),
         L.ptr(ne), 0 if ne is None else ne.shape[0], L.ptr(cre), 0 if cre is None else cre.shape[0],
         n_real, L.ptr(res.get('dm')), L.ptr(res.get('fd')), L.ptr(res.get('I')),
         L.ptr(res.get('Q')), L.ptr(res.get('U')), L.stream_ptr()))

@@ -106,7 +106,7 @@ class PeerExchange:
 
 class EnsembleEvaluator:
     def __init__(self, box, resolution, nside, los_settings, quantities=('fd', 'dm', 'I', 'Q', 'U'),
-                 n_real=1, rank=0, world=1, b_stride=16, group=None, exchange='auto'):
+                 n_real=1, rank=0, world=1, b_stride='auto', group=None, exchange='auto'):
         import torch
         self.torch = torch
         self.grid = engine.DeviceGrid(box, resolution)
@@ -119,7 +119,7 @@ class EnsembleEvaluator:
         self.rank, self.world, self.group = int(rank), int(world), group
         self.lo, self.hi = shard_bounds(self.n_real, self.rank, self.world)
         self.n_local = self.hi - self.lo
-        self.b_stride = int(b_stride)
+        self.b_stride = engine.pick_b_stride(self.n_local) if b_stride == 'auto' else int(b_stride)
         self.dirs = engine.healpix_ring_dirs(self.nside)
         self._field_bufs = {}
         dev = self.dirs.device

@@ -59,35 +59,36 @@ DESCS = [(OF.CONST_B, [0.0, 1.0, 0.0], 0), (OF.GAUSS_B, [0.0, 2.0], 1),
          (OF.EXP_NE, [0.01, 3.0, 0.1], 2), (OF.CRE_ANALYTIC, [0.0217, 5.0, 1.0, 8.3], 3)]
 
 
-@pytest.mark.parametrize('bs', [3, 4, 16])
-@pytest.mark.parametrize('N', [1, 2, 3, 5, 8, 17])
+@pytest.mark.parametrize('bs', [3, 4, 16, 48, 96])
+@pytest.mark.parametrize('N', [1, 2, 3, 5, 8, 17, 33])
 def test_all_observables_match_oracle(eng, bs, N):
     maps, omaps = _run(eng, [20, 18, 12], DESCS, list(range(50, 50 + N)), 4, bs, dict(dr=0.2))
     _check(maps, omaps)
 
 
-@pytest.mark.parametrize('bs', [4, 16])
+@pytest.mark.parametrize('bs', [4, 16, 48, 96])
 def test_nside16_grid32_23ghz(eng, bs):
     maps, omaps = _run(eng, [32, 32, 16], DESCS, [7, 8, 9, 10, 11, 12], 16, bs, dict(dr=0.1))
     _check(maps, omaps)
 
 
-def test_interleaved_layout_variants(eng):
-    """b_stride 16 through every kernel variant: Faraday only, sync only, variable index, random n_e."""
-    maps, omaps = _run(eng, [20, 18, 12], DESCS[:3], [1, 2, 3, 4, 5], 4, 16, dict(dr=0.2), want=('dm', 'fd'))
+@pytest.mark.parametrize('il', [16, 48, 96])
+def test_interleaved_layout_variants(eng, il):
+    """Interleaved layouts through every kernel variant: Faraday only, sync only, variable index, random n_e."""
+    maps, omaps = _run(eng, [20, 18, 12], DESCS[:3], [1, 2, 3, 4, 5], 4, il, dict(dr=0.2), want=('dm', 'fd'))
     _check(maps, omaps, ('dm', 'fd'))
     d = [DESCS[0], DESCS[1], DESCS[3]]
-    maps, omaps = _run(eng, [20, 18, 12], d, [1, 2, 3, 4, 5, 6, 7], 4, 16, dict(dr=0.2), want=('I', 'Q', 'U'))
+    maps, omaps = _run(eng, [20, 18, 12], d, [1, 2, 3, 4, 5, 6, 7], 4, il, dict(dr=0.2), want=('I', 'Q', 'U'))
     _check(maps, omaps, ('I', 'Q', 'U'))
-    maps, omaps = _run(eng, [20, 18, 12], DESCS, list(range(1, 10)), 4, 16,
+    maps, omaps = _run(eng, [20, 18, 12], DESCS, list(range(1, 10)), 4, il,
                        dict(dr=0.2, alpha=2.7, beta=0.02, theta=-0.05, nu_ghz=2.3))
     _check(maps, omaps)
     descs = DESCS[:2] + [(OF.RANDOM_NE, [0.02, 0.01, 0.0], 4), DESCS[3]]
-    maps, omaps = _run(eng, [16, 16, 8], descs, [1, 2, 3, 4, 5, 6], 4, 16, dict(dr=0.2))
+    maps, omaps = _run(eng, [16, 16, 8], descs, [1, 2, 3, 4, 5, 6], 4, il, dict(dr=0.2))
     _check(maps, omaps)
     # the layouts agree with each other bit for bit on the fields and to rounding on the maps
     a, _ = _run(eng, [20, 18, 12], DESCS, [1, 2, 3, 4, 5], 4, 4, dict(dr=0.2))
-    b, _ = _run(eng, [20, 18, 12], DESCS, [1, 2, 3, 4, 5], 4, 16, dict(dr=0.2))
+    b, _ = _run(eng, [20, 18, 12], DESCS, [1, 2, 3, 4, 5], 4, il, dict(dr=0.2))
     for k in KEYS:
         assert np.allclose(a[k], b[k], rtol=1e-11, atol=1e-13 * np.abs(a[k]).max()), k
 
