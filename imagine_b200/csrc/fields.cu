@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) field_b_il4_kernel(const __grid_constant_
   }
 }
 
-// ---- magnetic field, wide realisation-interleaved layout (b_stride 3*RL, RL = 32 | 16) ---------
+// ---- magnetic field, wide realisation-interleaved layout (b_stride 3*RL, RL = 32 | 16 | 8) ---------
 // out[group][cell][component][RL], group = r / RL: what the lane-per-realisation LOS kernel
 // (los_rl.cu) reads with one coalesced 64-bit load per corner component.  Thread = (pair of cells,
 // realisation), realisation fastest, so each of the six stores of a warp is RL*8 contiguous bytes.
@@ -448,7 +448,8 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
   DevGrid g;
   IMB_TRY(make_dev_grid(grid, &g));
   if (!fields || nfields < 0 || n_real < 1) return IMB_EINVAL;
-  if (out_B && b_stride != 3 && b_stride != 4 && b_stride != 16 && b_stride != 48 && b_stride != 96)
+  if (out_B && b_stride != 3 && b_stride != 4 && b_stride != 16 && b_stride != 24 && b_stride != 48 &&
+      b_stride != 96)
     return IMB_EINVAL;
   for (int f = 0; f < nfields; ++f)
     if (field_type(fields[f].kind) < 0) return IMB_EINVAL;
@@ -511,7 +512,7 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
         int bx = grid_blocks(work4, 256, 8) / n_groups;
         if (bx < 1) bx = 1;
         field_b_il4_kernel<<<dim3(bx, n_groups), 256, 0, stream>>>(a, outs[type]);
-      } else if (b_stride == 48 || b_stride == 96) {
+      } else if (b_stride == 24 || b_stride == 48 || b_stride == 96) {
         // wide interleave: [ceil(rows/RL), ncell, 3, RL]
         const int rl = b_stride / 3;
         if (need != n_real || addr % 32 != 0) return IMB_EINVAL;
@@ -520,7 +521,8 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
         int bx = grid_blocks(((g.ncell + 1) / 2) * rl, 256, 8) / n_groups;
         if (bx < 1) bx = 1;
         if (rl == 32) field_b_rl_kernel<32><<<dim3(bx, n_groups), 256, 0, stream>>>(a, outs[type]);
-        else field_b_rl_kernel<16><<<dim3(bx, n_groups), 256, 0, stream>>>(a, outs[type]);
+        else if (rl == 16) field_b_rl_kernel<16><<<dim3(bx, n_groups), 256, 0, stream>>>(a, outs[type]);
+        else field_b_rl_kernel<8><<<dim3(bx, n_groups), 256, 0, stream>>>(a, outs[type]);
       } else if (b_stride == 3) {
         const bool vec = (addr % 16 == 0) && (need == 1 || row_elems % 2 == 0);
         if (vec) field_b_kernel<3, true><<<blocks, 256, 0, stream>>>(a, outs[type]);

@@ -401,7 +401,7 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
   IMB_TRY(make_dev_grid(grid, &a.g));
   if (m == 0 && cfg && n_real >= 1) return IMB_OK;            // nothing to integrate
   if (!cfg || !dirs || !B || m < 0 || n_real < 1) return IMB_EINVAL;
-  if (b_stride != 3 && b_stride != 4 && b_stride != 16 && b_stride != 48 && b_stride != 96)
+  if (b_stride != 3 && b_stride != 4 && b_stride != 16 && b_stride != 24 && b_stride != 48 && b_stride != 96)
     return IMB_EINVAL;
   if (b_stride >= 4 && (reinterpret_cast<uintptr_t>(B) % 32 != 0)) return IMB_EINVAL;
   if (b_stride >= 16 && rows_B != n_real) return IMB_EINVAL;   // interleaved layouts are per realisation
@@ -482,7 +482,7 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
     rt = n_real >= 4 ? 4 : (n_real >= 2 ? 2 : 1);
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (b_stride == 48 || b_stride == 96) {     // lane = realisation (los_rl.cu)
+  if (b_stride == 24 || b_stride == 48 || b_stride == 96) {     // lane = realisation (los_rl.cu)
     IMB_TRY(launch_los_rl(a, b_stride / 3, has_ne, has_cre, var_p, s));
     IMB_LAUNCHED();
     return IMB_OK;

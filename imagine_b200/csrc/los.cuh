@@ -43,6 +43,13 @@ __device__ __forceinline__ double4 ldg256(const double* p) {
   return v;
 }
 
+// volatile: the compiler keeps these loads in program order, ahead of the arithmetic that follows
+__device__ __forceinline__ double ldg64(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ double lerp(double a, double b, double t) { return fma(t, b - a, a); }
 
 struct Cell {
@@ -99,6 +106,28 @@ __device__ __forceinline__ void interp_vector(const double* __restrict__ f, cons
   bx = lerp(lerp(x00, x01, c.ty), lerp(x10, x11, c.ty), c.tx);
   by = lerp(lerp(y00, y01, c.ty), lerp(y10, y11, c.ty), c.tx);
   bz = lerp(lerp(z00, z01, c.ty), lerp(z10, z11, c.ty), c.tx);
+}
+
+// sin and cos of a moderate argument with constant-bank coefficients (kSinC / kCosC): two-constant
+// Cody-Waite reduction by pi/2 + the Taylor kernels of common.cuh, <= 2 ulp for |x| < 1e5.  The CUDA
+// library sincos() materialises every coefficient through a pair of uniform moves (~34 UMOV per
+// call in the ray-march loop, ncu source page); huge or non-finite arguments still go there.
+__device__ __forceinline__ void sincos_cw(double x, double& sn, double& cs) {
+  if (!(fabs(x) < 1.0e5)) { sincos(x, &sn, &cs); return; }
+  const int q = __double2int_rn(x * 0.6366197723675814);
+  const double kf = (double)q;
+  double r = fma(-kf, 1.5707963267948966, x);
+  r = fma(-kf, 6.123233995736766e-17, r);
+  const double z = r * r;
+  double ps = kSinC[6], pc = kCosC[7];
+#pragma unroll
+  for (int k = 5; k >= 0; --k) ps = fma(ps, z, kSinC[k]);
+#pragma unroll
+  for (int k = 6; k >= 0; --k) pc = fma(pc, z, kCosC[k]);
+  const double s0 = fma(r * z, ps, r), c0 = fma(z, pc, 1.0);
+  const double s1 = (q & 1) ? c0 : s0, c1 = (q & 1) ? s0 : c0;
+  sn = (q & 2) ? -s1 : s1;
+  cs = ((q + 1) & 2) ? -c1 : c1;
 }
 
 __device__ __forceinline__ double sync_coeff_var(const LosArgs& a, double p) {

@@ -1,5 +1,5 @@
 // Stage 2, realisation-lane kernel: line-of-sight integration over the wide realisation-interleaved
-// layout B[group][cell][component][RL] (b_stride 3*RL, RL = 32 or 16 realisations per group).
+// layout B[group][cell][component][RL] (b_stride 3*RL, RL = 32, 16 or 8 realisations per group).
 //
 // los_il4s_kernel (lane = 4*sample + realisation) is bound by the L1 data pipe (ncu: 84-86 % of
 // the wavefront peak): every 256-bit corner gather costs the 8-wavefront minimum, a quarter of the
@@ -14,8 +14,9 @@
 //     only in-box steps are marched (ballot mask);
 //   * the ray accumulators (Faraday depth, I, Q, U) are plain registers: no scan, no shuffles, no
 //     shared-memory read-modify-write in the loop;
-//   * RL = 16: the two half-warps march the two halves of the ray; the outer half is rotated by the
-//     inner half's total Faraday depth when the halves are joined (the rotation is linear in Q+iU).
+//   * RL = 16 / 8: the 2 / 4 lane groups march consecutive segments of the ray; when the segments are
+//     joined, each outer one is rotated by the total Faraday depth of those inside it (the rotation
+//     is linear in Q+iU).
 // Numeric definition: oracle/los.py.
 #include <cstdlib>
 #include "los.cuh"
@@ -156,25 +157,27 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
       const double* p = Bg + (long long)base * CS;
       double bx, by, bz;
       {
-        // four z-pairs per component, each reduced as soon as it lands
-        double a0, a1, a2, b0, b1, b2;
-        a0 = __ldg(p); a1 = __ldg(p + RL); a2 = __ldg(p + 2 * RL);
-        b0 = __ldg(p + CS); b1 = __ldg(p + CS + RL); b2 = __ldg(p + CS + 2 * RL);
-        double x00 = lerp(a0, b0, tz), y00 = lerp(a1, b1, tz), z00 = lerp(a2, b2, tz);
-        const double* py_ = p + oy;
-        a0 = __ldg(py_); a1 = __ldg(py_ + RL); a2 = __ldg(py_ + 2 * RL);
-        b0 = __ldg(py_ + CS); b1 = __ldg(py_ + CS + RL); b2 = __ldg(py_ + CS + 2 * RL);
-        double x01 = lerp(a0, b0, tz), y01 = lerp(a1, b1, tz), z01 = lerp(a2, b2, tz);
+        // all 24 corner loads are issued before the first lerp: one exposed memory round trip per
+        // step instead of one per z-pair (ncu source page: the stall samples sat on the first use
+        // after each group of six loads)
+        const double* q1 = p + oy;
+        const double* q2 = p + ox;
+        const double* q3 = q2 + oy;
+        double v0[6], v1[6], v2[6], v3[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v0[k] = ldg64(p + (k / 3) * CS + (k % 3) * RL);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v1[k] = ldg64(q1 + (k / 3) * CS + (k % 3) * RL);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v2[k] = ldg64(q2 + (k / 3) * CS + (k % 3) * RL);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v3[k] = ldg64(q3 + (k / 3) * CS + (k % 3) * RL);
+        double x00 = lerp(v0[0], v0[3], tz), y00 = lerp(v0[1], v0[4], tz), z00 = lerp(v0[2], v0[5], tz);
+        const double x01 = lerp(v1[0], v1[3], tz), y01 = lerp(v1[1], v1[4], tz), z01 = lerp(v1[2], v1[5], tz);
         x00 = lerp(x00, x01, ty); y00 = lerp(y00, y01, ty); z00 = lerp(z00, z01, ty);
-        const double* px_ = p + ox;
-        a0 = __ldg(px_); a1 = __ldg(px_ + RL); a2 = __ldg(px_ + 2 * RL);
-        b0 = __ldg(px_ + CS); b1 = __ldg(px_ + CS + RL); b2 = __ldg(px_ + CS + 2 * RL);
-        double x10 = lerp(a0, b0, tz), y10 = lerp(a1, b1, tz), z10 = lerp(a2, b2, tz);
-        const double* pxy = px_ + oy;
-        a0 = __ldg(pxy); a1 = __ldg(pxy + RL); a2 = __ldg(pxy + 2 * RL);
-        b0 = __ldg(pxy + CS); b1 = __ldg(pxy + CS + RL); b2 = __ldg(pxy + CS + 2 * RL);
-        x01 = lerp(a0, b0, tz); y01 = lerp(a1, b1, tz); z01 = lerp(a2, b2, tz);
-        x10 = lerp(x10, x01, ty); y10 = lerp(y10, y01, ty); z10 = lerp(z10, z01, ty);
+        double x10 = lerp(v2[0], v2[3], tz), y10 = lerp(v2[1], v2[4], tz), z10 = lerp(v2[2], v2[5], tz);
+        const double x11 = lerp(v3[0], v3[3], tz), y11 = lerp(v3[1], v3[4], tz), z11 = lerp(v3[2], v3[5], tz);
+        x10 = lerp(x10, x11, ty); y10 = lerp(y10, y11, ty); z10 = lerp(z10, z11, ty);
         bx = lerp(x00, x10, tx); by = lerp(y00, y10, tx); bz = lerp(z00, z10, tx);
       }
       Cell c;
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
           I += em;
           if (HAS_NE) {
             double sa, ca;
-            sincos(2.0 * phi * a.lam2, &sa, &ca);
+            sincos_cw(2.0 * phi * a.lam2, sa, ca);
             Q += qc * ca - uc * sa;
             U += qc * sa + uc * ca;
           } else {
@@ -274,7 +277,8 @@ template <int RL, bool HAS_NE, bool HAS_CRE, bool VAR_P, bool P3>
 static int launch_rl_variant(const LosArgs& a, cudaStream_t s) {
   const int n_groups = (a.n_real + RL - 1) / RL;
   dim3 grid((a.m + 7) / 8, n_groups);
-  int minb = 4;                      // 64 registers, 32 warps / SM: measured best (3.67 vs 3.79 ms at C3)
+  // measured at C3 (64 realisations): RL 32 -> 80 registers (3.40 vs 3.69 ms), RL 16 -> 64 (3.84 vs 4.01)
+  int minb = RL == 32 ? 3 : 4;
   if (const char* e = getenv("IMB_LOS_MINB")) minb = atoi(e);
   if (minb >= 4) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, 4><<<grid, 256, 0, s>>>(a);
   else if (minb == 3) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, 3><<<grid, 256, 0, s>>>(a);
@@ -296,11 +300,12 @@ static int launch_rl(const LosArgs& a, bool has_ne, bool has_cre, bool var_p, cu
             : launch_rl_variant<RL, false, true, false, false>(a, s);
 }
 
-// entry used by imb_los_integrate for b_stride == 96 (RL 32) and 48 (RL 16)
+// entry used by imb_los_integrate for b_stride == 96 (RL 32), 48 (RL 16) and 24 (RL 8)
 int launch_los_rl(const LosArgs& a, int rl, bool has_ne, bool has_cre, bool var_p, cudaStream_t s) {
   if (a.g.ncell >= (1ll << 31)) return IMB_EUNSUPPORTED;      // 32-bit cell index in RlGeo
-  return rl == 32 ? launch_rl<32>(a, has_ne, has_cre, var_p, s)
-                  : launch_rl<16>(a, has_ne, has_cre, var_p, s);
+  if (rl == 32) return launch_rl<32>(a, has_ne, has_cre, var_p, s);
+  if (rl == 16) return launch_rl<16>(a, has_ne, has_cre, var_p, s);
+  return launch_rl<8>(a, has_ne, has_cre, var_p, s);
 }
 
 }  // namespace imb

@@ -80,17 +80,16 @@ def field_rows(descs, n_real):
 FIELD_NAMES = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
 
 
-INTERLEAVED_STRIDES = (16, 48, 96)
+INTERLEAVED_STRIDES = (16, 24, 48, 96)
 
 
 def pick_b_stride(n_real):
     """Widest realisation interleave a block of `n_real` realisations fills without padding:
-    96 = [group][cell][3][32] and 48 = [group][cell][3][16] (lane-per-realisation LOS kernel,
-    los_rl.cu), else 16 = [group][cell][4][4] (los_il4.cu)."""
-    if n_real % 32 == 0:
-        return 96
-    if n_real % 16 == 0:
-        return 48
+    96 / 48 / 24 = [group][cell][3][32 / 16 / 8] (lane-per-realisation LOS kernel, los_rl.cu), else
+    16 = [group][cell][4][4] (los_il4.cu)."""
+    for rl in (32, 16, 8):
+        if n_real % rl == 0:
+            return 3 * rl
     return 16
 
 
@@ -98,7 +97,7 @@ def b_shape(rows, ncell, b_stride):
     """Shape of the magnetic-field buffer for a layout code."""
     if b_stride == 16:
         return ((rows + 3) // 4, ncell, 4, 4)           # [group][cell][realisation % 4][x,y,z,0]
-    if b_stride in (48, 96):
+    if b_stride in (24, 48, 96):
         rl = b_stride // 3
         return ((rows + rl - 1) // rl, ncell, 3, rl)    # [group][cell][x|y|z][realisation % RL]
     return (rows, ncell, b_stride)
