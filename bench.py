@@ -178,6 +178,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--points', type=int, default=8, help='parameter points per pipelined flush (extra key)')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'peer', 'alltoall', 'allgather'])
+    ap.add_argument('--profile-e2e', action='store_true', help='cProfile the plugin-API loop (stderr)')
     ap.add_argument('--b-stride', default='auto', help="field layout: 'auto' | 16 | 48 | 96 (A/B runs)")
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -318,16 +319,26 @@ def main():
         if any(q in quantities for q in 'IQU'):
             fields.append(api.AnalyticCosmicRayElectrons(api_grid, parameters={
                 'j0': 0.0217, 'r0': 5.0 * u.kpc, 'z0': 1.0 * u.kpc, 'r_sun': 8.3 * u.kpc}, ensemble_size=N))
-        api_lik._reset_device_state()                 # measurements/variances re-uploaded from host
-        return float(api_lik(api_sim(fields)))
+        sims = api_sim(fields)
+        api_lik.upload_measurements()     # measurements/variances re-uploaded from pinned host memory
+        return float(api_lik(sims))
 
     e2e_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
     e0.record()
+    prof = None
+    if args.profile_e2e and rank == 0:
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     for _ in range(args.steps):
         e2e_val = e2e_step()
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats('cumulative').print_stats(45)
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 0.0)

@@ -45,22 +45,66 @@ class _DeviceLikelihoodMixin:
 
     def _reset_device_state(self):
         self._dev_meas, self._dev_cov, self._dev_keep = {}, {}, {}
+        self._pinned = {}
         self._shard_bufs = {}
+        self._copy_stream, self._upload_event, self._last_use = None, None, None
+
+    def _host_array(self, kind, key):
+        if kind == 'meas':
+            return np.ascontiguousarray(self._measurement_dict[key].data[0], dtype=np.float64)
+        obs = self._covariance_dict[key]
+        return np.ascontiguousarray(obs.var if obs.dtype == 'variance' else obs.data, dtype=np.float64)
+
+    def upload_measurements(self):
+        """
+        (Re-)upload measurements and variances from pinned host memory, asynchronously on a copy
+        stream, so the transfer overlaps whatever the caller launches next (normally the
+        simulator).  The next `call` waits for it on the device only.  Dense covariances keep
+        the lazy, blocking upload (they are too large to pin per Likelihood).
+        """
+        t = _torch()
+        if self._copy_stream is None:
+            self._copy_stream = t.cuda.Stream()
+        jobs = []
+        for kind, store in (('meas', self._dev_meas), ('cov', self._dev_cov)):
+            if kind == 'cov' and self._covariance_dict is None:
+                continue
+            source = self._measurement_dict if kind == 'meas' else self._covariance_dict
+            for key in source.keys():
+                if kind == 'cov' and source[key].dtype != 'variance':
+                    continue
+                pin = self._pinned.get((kind, key))
+                if pin is None:
+                    pin = t.from_numpy(self._host_array(kind, key)).pin_memory()
+                    self._pinned[(kind, key)] = pin
+                if key not in store:
+                    store[key] = t.empty(pin.shape, dtype=t.float64, device='cuda')
+                jobs.append((store[key], pin))
+        # the buffers may still be read by the previous evaluation (not by work queued since, e.g.
+        # the simulator kernels of this one: waiting for those would serialise the copy behind them)
+        if self._last_use is not None:
+            self._copy_stream.wait_event(self._last_use)
+        with t.cuda.stream(self._copy_stream):
+            for dev, pin in jobs:
+                dev.copy_(pin, non_blocking=True)
+            self._upload_event = self._copy_stream.record_event()
+
+    def _await_upload(self):
+        if self._upload_event is not None:
+            _torch().cuda.current_stream().wait_event(self._upload_event)
+            self._upload_event = None
 
     def _measured(self, key):
+        self._await_upload()
         if key not in self._dev_meas:
-            t = _torch()
-            self._dev_meas[key] = t.from_numpy(
-                np.ascontiguousarray(self._measurement_dict[key].data[0], dtype=np.float64)).cuda()
+            self._dev_meas[key] = _torch().from_numpy(self._host_array('meas', key)).cuda()
         return self._dev_meas[key]
 
     def _covariance(self, key):
         """[m] for the 'variance' dtype (never expanded with np.diag), [m,m] otherwise."""
+        self._await_upload()
         if key not in self._dev_cov:
-            t = _torch()
-            obs = self._covariance_dict[key]
-            host = obs.var if obs.dtype == 'variance' else obs.data
-            self._dev_cov[key] = t.from_numpy(np.ascontiguousarray(host, dtype=np.float64)).cuda()
+            self._dev_cov[key] = _torch().from_numpy(self._host_array('cov', key)).cuda()
         return self._dev_cov[key]
 
     def _variance(self, key):
@@ -98,10 +142,16 @@ class _DeviceLikelihoodMixin:
         observable_dict = self._masked_simulations(observable_dict)
         value = self.call(observable_dict, **kwargs)
         if not self.compute_dispersion:
+            self._mark_last_use()
             return value
         sample = [self._bootstrapped_likelihood(observable_dict, **kwargs)
                   for _ in range(self.n_bootstrap)]
+        self._mark_last_use()
         return value, np.std(sample)
+
+    def _mark_last_use(self):
+        if self._copy_stream is not None:
+            self._last_use = _torch().cuda.current_stream().record_event()
 
     def _bootstrapped_likelihood(self, simulations, **kwargs):
         # likelihood.py:94-100: rows resampled with replacement (on the device)
@@ -116,8 +166,9 @@ class _DeviceLikelihoodMixin:
 
     def __getstate__(self):
         state = dict(self.__dict__)
-        for k in ('_dev_meas', '_dev_cov', '_dev_keep', '_shard_bufs'):
+        for k in ('_dev_meas', '_dev_cov', '_dev_keep', '_shard_bufs', '_pinned'):
             state[k] = {}
+        state['_copy_stream'] = state['_upload_event'] = state['_last_use'] = None
         return state
 
 

@@ -249,6 +249,15 @@ def test_full_drop_in_evaluation_and_units(api):
     assert lk2(sim2(fields)) == value
     host_sims = pickle.loads(pickle.dumps(sims[keys[0]]))
     assert np.array_equal(host_sims.data, sims[keys[0]].data)
+    # asynchronous re-upload from pinned host memory (overlaps the simulator) changes nothing,
+    # before or after the first evaluation, and the likelihood still pickles afterwards
+    lk3 = api.B200EnsembleLikelihood(meas)
+    for _ in range(3):
+        lk3.upload_measurements()
+        assert lk3(sim(fields)) == value
+    assert pickle.loads(pickle.dumps(lk3))(sims) == value
+    lkm.upload_measurements()
+    assert abs(lkm(sims) - want) <= 1e-8 * max(1.0, abs(want))
 
 
 def test_gpu_fields_serve_host_consumers(api):
