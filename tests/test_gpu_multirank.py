@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 BOX = [[-20.0, 20.0], [-20.0, 20.0], [-4.0, 4.0]]
 QUANT = ('fd', 'dm', 'I', 'Q', 'U')
 DESCS = [(3, [0.01, 3.0, 0.5], 0), (0, [0.0, 1.0, 0.0], 1), (1, [0.0, 2.0], 2), (6, [0.0217, 5.0, 1.0, 8.3], 3)]
-N, NSIDE, RES = 8, 8, [24, 24, 12]
+# 16 realisations: one GPU marches them 16 wide (b_stride 48), two GPUs 8 wide (b_stride 24)
+N, NSIDE, RES = 16, 8, [24, 24, 12]
 
 
 def _setup(rank, world, exchange):
@@ -105,11 +106,13 @@ def test_two_gpu_paths_match_single_gpu():
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, out in results:
-        assert out['allgather'] == want                                   # bit-identical maps, same kernels
+        # same realisations, other ray segmentation (layout follows the shard size): rounding only
+        assert abs(out['allgather'] - want) <= 1e-9 * max(1.0, abs(want))
         assert abs(out['alltoall'] - want) <= 1e-9 * max(1.0, abs(want))  # different summation order
         assert out['peer'] == out['alltoall']                             # fused NVLink exchange: same data, same kernels
         assert out['plugin_sharded'] == 'ShardedDeviceObservable'
         assert abs(out['plugin'] - want_plugin) <= 1e-9 * max(1.0, abs(want_plugin))
-        assert np.array_equal(out['plugin_full_Q'], sims1[('sync', 23.0, NSIDE, 'Q')].data)
+        q1 = sims1[('sync', 23.0, NSIDE, 'Q')].data
+        assert np.allclose(out['plugin_full_Q'], q1, rtol=1e-9, atol=1e-12 * np.abs(q1).max())
     assert results[0][1]['alltoall'] == results[1][1]['alltoall']         # replicated scalar
     assert results[0][1]['plugin'] == results[1][1]['plugin']
