@@ -19,7 +19,30 @@ struct FieldArgs {
   double p[IMB_MAX_FIELDS][8];
   int n_real;                       // seeds row length
   const unsigned long long* seeds;  // device [n_seed_rows, n_real]
+  // fast path of the magnetic-field kernels: constant fields followed by ONE Gaussian field (or
+  // any order when there are just two: the sum commutes).  csum = the constants added in list
+  // order on the host (same IEEE additions the generic loop does), gauss = index of the Gaussian.
+  int simple, has_const, gauss;
+  double csum[3];
 };
+
+// the six normals of cell pair q of one realisation: v = [csum +] (z sigma + mu)
+__device__ __forceinline__ void simple_pair(const FieldArgs& a, unsigned long long seed, unsigned int q,
+                                            double* v) {
+  const double mu = a.p[a.gauss][0], sigma = a.p[a.gauss][1];
+  const unsigned int stream = a.stream[a.gauss];
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    double z0, z1;
+    philox_normal_pair(seed, stream, 3ull * q + b, z0, z1);
+    v[2 * b] = __dadd_rn(__dmul_rn(z0, sigma), mu);
+    v[2 * b + 1] = __dadd_rn(__dmul_rn(z1, sigma), mu);
+  }
+  if (a.has_const) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = __dadd_rn(a.csum[k % 3], v[k]);
+  }
+}
 
 __device__ __forceinline__ void cell_xyz(const DevGrid& g, long long c, double& x, double& y,
                                          double& z) {
@@ -132,6 +155,21 @@ __global__ void __launch_bounds__(256) field_b_il4_kernel(const __grid_constant_
   // grid = (pair blocks, realisation groups): all index arithmetic stays 32-bit (no 64-bit division)
   const unsigned int npair4 = (unsigned int)((a.g.ncell + 1) >> 1) * 4u;
   const int g = blockIdx.y;
+  if (a.simple) {
+    const int r4 = (int)(threadIdx.x & 3u), r = g * 4 + r4;
+    const bool live = r < a.rows;
+    const unsigned long long seed = live ? a.seeds[(size_t)a.seed_row[a.gauss] * a.n_real + r] : 0ull;
+    for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < npair4; w += gridDim.x * blockDim.x) {
+      const unsigned int q = w >> 2;
+      double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      if (live) simple_pair(a, seed, q, v);
+      const long long c0 = 2ll * q;
+      double* o = out + (((long long)g * a.g.ncell + c0) * 4 + r4) * 4;
+      *reinterpret_cast<double4*>(o) = make_double4(v[0], v[1], v[2], 0.0);
+      if (c0 + 1 < a.g.ncell) *reinterpret_cast<double4*>(o + 16) = make_double4(v[3], v[4], v[5], 0.0);
+    }
+    return;
+  }
   for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < npair4; w += gridDim.x * blockDim.x) {
     const int r4 = (int)(w & 3u);
     const unsigned int q = w >> 2;
@@ -178,6 +216,22 @@ __global__ void __launch_bounds__(256) field_b_rl_kernel(const __grid_constant__
                                                          double* __restrict__ out) {
   const unsigned int npair_rl = (unsigned int)((a.g.ncell + 1) >> 1) * (unsigned int)RL;
   const int g = blockIdx.y;
+  if (a.simple) {
+    // the grid stride is a multiple of RL: realisation and seed are fixed per thread
+    const int rl = (int)(threadIdx.x % RL), r = g * RL + rl;
+    const bool live = r < a.rows;
+    const unsigned long long seed = live ? a.seeds[(size_t)a.seed_row[a.gauss] * a.n_real + r] : 0ull;
+    for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < npair_rl; w += gridDim.x * blockDim.x) {
+      const unsigned int q = w / RL;
+      double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      if (live) simple_pair(a, seed, q, v);
+      const long long c0 = 2ll * q;
+      double* o = out + ((long long)g * a.g.ncell + c0) * (3 * RL) + rl;
+      o[0] = v[0]; o[RL] = v[1]; o[2 * RL] = v[2];
+      if (c0 + 1 < a.g.ncell) { o[3 * RL] = v[3]; o[4 * RL] = v[4]; o[5 * RL] = v[5]; }
+    }
+    return;
+  }
   for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < npair_rl; w += gridDim.x * blockDim.x) {
     const int rl = (int)(w % RL);
     const unsigned int q = w / RL;
@@ -497,6 +551,21 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
       a.seed_row[a.nfields] = fields[f].seed_row;
       for (int k = 0; k < 8; ++k) a.p[a.nfields][k] = fields[f].p[k];
       a.nfields++;
+    }
+    a.simple = a.has_const = a.gauss = 0;
+    a.csum[0] = a.csum[1] = a.csum[2] = 0.0;
+    if (type == 0) {
+      int n_gauss = 0, n_const = 0;
+      for (int f = 0; f < a.nfields; ++f) {
+        if (a.kind[f] == IMB_FIELD_GAUSS_B) { n_gauss++; a.gauss = f; }
+        if (a.kind[f] == IMB_FIELD_CONST_B) {
+          for (int k = 0; k < 3; ++k) a.csum[k] = n_const ? a.csum[k] + a.p[f][k] : a.p[f][k];
+          n_const++;
+        }
+      }
+      a.has_const = n_const > 0;
+      a.simple = n_gauss == 1 && n_gauss + n_const == a.nfields &&
+                 (a.gauss == a.nfields - 1 || a.nfields == 2);
     }
     const long long work = ((g.ncell + 1) / 2) * need;
     const int blocks = grid_blocks(work, 256, 8);

@@ -23,7 +23,7 @@
 
 namespace imb {
 
-struct RlPix {             // per warp, in shared memory
+struct __align__(16) RlPix {   // per warp, in shared memory; n|north|east re-read as four 128-bit words
   double n[3], north[3], east[2];
   int j_lo, j_hi;
 };
@@ -150,10 +150,13 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
     }
     for (; todo; todo &= todo - 1) {
       const int sl = seg * RL + (__ffs(todo) - 1);
-      const RlGeo& ge = s_geo[warp][sl];
-      const int base = ge.base;
+      // three 128-bit broadcast reads: (tx, ty) (tz, n_e) (CRE, base)
+      const double2* gp = reinterpret_cast<const double2*>(&s_geo[warp][sl]);
+      const double2 g2 = gp[2];
+      const int base = __double2loint(g2.y);
       if (S > 1 && base < 0) continue;                  // the other segment's step, not mine
-      const double tx = ge.tx, ty = ge.ty, tz = ge.tz;
+      const double2 g0 = gp[0], g1 = gp[1];
+      const double tx = g0.x, ty = g0.y, tz = g1.x;
       const double* p = Bg + (long long)base * CS;
       double bx, by, bz;
       {
@@ -186,23 +189,27 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
       }
       double phi = 0.0;
       if (HAS_NE) {
-        double ne_s = ge.ne;
+        double ne_s = g1.y;
         if (!ne_shared) {
           ne_s = live ? interp_scalar(a.ne + a.ne_row * rr, c) : 0.0;
           dm += ne_s * a.dl_pc;
         }
-        const double bpar = -(bx * pc.n[0] + by * pc.n[1] + bz * pc.n[2]);
+        const double2* pp = reinterpret_cast<const double2*>(&pc);
+        const double2 n01 = pp[0], n2h = pp[1];
+        const double bpar = -(bx * n01.x + by * n01.y + bz * n2h.x);
         const double f = __dmul_rn(__dmul_rn(__dmul_rn(0.812, ne_s), bpar), a.dl_pc);
         phi = carry + 0.5 * f;
         carry += f;
       }
       if (HAS_CRE) {
-        double cre_s = ge.cre;
+        double cre_s = g2.x;
         if (!cre_shared) cre_s = live ? interp_scalar(a.cre + a.cre_row * rr, c) : 0.0;
         double kp = a.sync_k, pif = a.pol_frac, expo = a.expo;
         if (VAR_P) { kp = s_var[warp][sl][0]; pif = s_var[warp][sl][1]; expo = s_var[warp][sl][2]; }
-        const double bn = bx * pc.north[0] + by * pc.north[1] + bz * pc.north[2];
-        const double be = bx * pc.east[0] + by * pc.east[1];
+        const double2* pp = reinterpret_cast<const double2*>(&pc);
+        const double2 h0 = pp[1], h12 = pp[2], e01 = pp[3];          // (n2, north0) (north1, north2) east
+        const double bn = bx * h0.y + by * h12.x + bz * h12.y;
+        const double be = bx * e01.x + by * e01.y;
         const double bn2 = bn * bn, be2 = be * be, bp2 = bn2 + be2;
         if (bp2 > 0.0) {
           double em, qc, uc;
