@@ -146,126 +146,70 @@ __global__ void __launch_bounds__(256) field_b_kernel(const __grid_constant__ Fi
   }
 }
 
-// ---- magnetic field, realisation-interleaved layout (b_stride 16) ------------------------
-// out[group][cell][r4][4], group = r / 4, r4 = r % 4: the four realisations of a vertex share one
-// 128-byte line (what the LOS kernel's 4-lanes-per-sample gathers want).  Thread = (pair of
-// cells, realisation), r4 fastest, so a warp writes 2 KB contiguous.
-__global__ void __launch_bounds__(256) field_b_il4_kernel(const __grid_constant__ FieldArgs a,
-                                                          double* __restrict__ out) {
-  // grid = (pair blocks, realisation groups): all index arithmetic stays 32-bit (no 64-bit division)
-  const unsigned int npair4 = (unsigned int)((a.g.ncell + 1) >> 1) * 4u;
-  const int g = blockIdx.y;
-  if (a.simple) {
-    const int r4 = (int)(threadIdx.x & 3u), r = g * 4 + r4;
-    const bool live = r < a.rows;
-    const unsigned long long seed = live ? a.seeds[(size_t)a.seed_row[a.gauss] * a.n_real + r] : 0ull;
-    for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < npair4; w += gridDim.x * blockDim.x) {
-      const unsigned int q = w >> 2;
-      double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      if (live) simple_pair(a, seed, q, v);
-      const long long c0 = 2ll * q;
-      double* o = out + (((long long)g * a.g.ncell + c0) * 4 + r4) * 4;
-      *reinterpret_cast<double4*>(o) = make_double4(v[0], v[1], v[2], 0.0);
-      if (c0 + 1 < a.g.ncell) *reinterpret_cast<double4*>(o + 16) = make_double4(v[3], v[4], v[5], 0.0);
-    }
-    return;
-  }
-  for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < npair4; w += gridDim.x * blockDim.x) {
-    const int r4 = (int)(w & 3u);
-    const unsigned int q = w >> 2;
-    const int r = g * 4 + r4;
-    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    if (r < a.rows) {
-      bool first = true;
-      for (int f = 0; f < a.nfields; ++f) {
-        double t[6];
-        if (a.kind[f] == IMB_FIELD_CONST_B) {
+// the same-type sum of all magnetic fields for cell pair q of realisation r (any field list)
+__device__ __forceinline__ void generic_pair(const FieldArgs& a, unsigned int q, int r, double* v) {
+  bool first = true;
+  for (int f = 0; f < a.nfields; ++f) {
+    double t[6];
+    if (a.kind[f] == IMB_FIELD_CONST_B) {
 #pragma unroll
-          for (int k = 0; k < 6; ++k) t[k] = a.p[f][k % 3];
-        } else if (a.kind[f] == IMB_FIELD_LSA_B) {
-          lsa_pair(a.g, a.p[f], 2ll * q, (2ll * q + 1) < a.g.ncell, t);
-        } else {
-          const unsigned long long seed = a.seeds[(size_t)a.seed_row[f] * a.n_real + r];
-          const double mu = a.p[f][0], sigma = a.p[f][1];
+      for (int k = 0; k < 6; ++k) t[k] = a.p[f][k % 3];
+    } else if (a.kind[f] == IMB_FIELD_LSA_B) {
+      lsa_pair(a.g, a.p[f], 2ll * q, (2ll * q + 1) < a.g.ncell, t);
+    } else {
+      const unsigned long long seed = a.seeds[(size_t)a.seed_row[f] * a.n_real + r];
+      const double mu = a.p[f][0], sigma = a.p[f][1];
 #pragma unroll
-          for (int b = 0; b < 3; ++b) {
-            double z0, z1;
-            philox_normal_pair(seed, a.stream[f], 3ull * q + b, z0, z1);
-            t[2 * b] = __dadd_rn(__dmul_rn(z0, sigma), mu);
-            t[2 * b + 1] = __dadd_rn(__dmul_rn(z1, sigma), mu);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) v[k] = first ? t[k] : __dadd_rn(v[k], t[k]);
-        first = false;
+      for (int b = 0; b < 3; ++b) {
+        double z0, z1;
+        philox_normal_pair(seed, a.stream[f], 3ull * q + b, z0, z1);
+        t[2 * b] = __dadd_rn(__dmul_rn(z0, sigma), mu);
+        t[2 * b + 1] = __dadd_rn(__dmul_rn(z1, sigma), mu);
       }
     }
-    const long long c0 = 2ll * q;
-    double* o = out + (((long long)g * a.g.ncell + c0) * 4 + r4) * 4;
-    *reinterpret_cast<double4*>(o) = make_double4(v[0], v[1], v[2], 0.0);
-    if (c0 + 1 < a.g.ncell) *reinterpret_cast<double4*>(o + 16) = make_double4(v[3], v[4], v[5], 0.0);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = first ? t[k] : __dadd_rn(v[k], t[k]);
+    first = false;
   }
 }
 
-// ---- magnetic field, wide realisation-interleaved layout (b_stride 3*RL, RL = 32 | 16 | 8) ---------
-// out[group][cell][component][RL], group = r / RL: what the lane-per-realisation LOS kernel
-// (los_rl.cu) reads with one coalesced 64-bit load per corner component.  Thread = (pair of cells,
-// realisation), realisation fastest, so each of the six stores of a warp is RL*8 contiguous bytes.
+// ---- magnetic field, realisation-interleaved layouts ---------------------------------------------
+// Thread = (pair of cells, realisation), realisation fastest; the grid stride is a multiple of the
+// interleave, so realisation and seed are fixed per thread.  Layouts (group = r / RL):
+//   RL 4  (b_stride 16):        out[group][cell][r % 4][x,y,z,0]: the four realisations of a vertex
+//                               share one 128-byte line (los_il4.cu); a warp writes 2 KB contiguous
+//   RL 32 | 16 | 8 (b_stride 3 RL): out[group][cell][component][r % RL]: one coalesced 64-bit load per
+//                               corner component for the lane-per-realisation LOS kernel (los_rl.cu)
+// (Measured and dropped: an 8-wide layout storing (B(cell), B(cell + 1 in z)) pairs so that a z-pair
+// of corners is one 128-bit load -- 4.95 vs 5.03 ms, twice the memory.)
 template <int RL>
-__global__ void __launch_bounds__(256) field_b_rl_kernel(const __grid_constant__ FieldArgs a,
+__global__ void __launch_bounds__(256) field_b_il_kernel(const __grid_constant__ FieldArgs a,
                                                          double* __restrict__ out) {
   const unsigned int npair_rl = (unsigned int)((a.g.ncell + 1) >> 1) * (unsigned int)RL;
   const int g = blockIdx.y;
-  if (a.simple) {
-    // the grid stride is a multiple of RL: realisation and seed are fixed per thread
-    const int rl = (int)(threadIdx.x % RL), r = g * RL + rl;
-    const bool live = r < a.rows;
-    const unsigned long long seed = live ? a.seeds[(size_t)a.seed_row[a.gauss] * a.n_real + r] : 0ull;
-    for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < npair_rl; w += gridDim.x * blockDim.x) {
-      const unsigned int q = w / RL;
-      double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      if (live) simple_pair(a, seed, q, v);
-      const long long c0 = 2ll * q;
-      double* o = out + ((long long)g * a.g.ncell + c0) * (3 * RL) + rl;
-      o[0] = v[0]; o[RL] = v[1]; o[2 * RL] = v[2];
-      if (c0 + 1 < a.g.ncell) { o[3 * RL] = v[3]; o[4 * RL] = v[4]; o[5 * RL] = v[5]; }
-    }
-    return;
-  }
+  const int rl = (int)(threadIdx.x % RL), r = g * RL + rl;
+  const bool live = r < a.rows;
+  const bool simple = a.simple != 0;
+  const unsigned long long seed =
+      (simple && live) ? a.seeds[(size_t)a.seed_row[a.gauss] * a.n_real + r] : 0ull;
   for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < npair_rl; w += gridDim.x * blockDim.x) {
-    const int rl = (int)(w % RL);
     const unsigned int q = w / RL;
-    const int r = g * RL + rl;
     double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    if (r < a.rows) {
-      bool first = true;
-      for (int f = 0; f < a.nfields; ++f) {
-        double t[6];
-        if (a.kind[f] == IMB_FIELD_CONST_B) {
-#pragma unroll
-          for (int k = 0; k < 6; ++k) t[k] = a.p[f][k % 3];
-        } else if (a.kind[f] == IMB_FIELD_LSA_B) {
-          lsa_pair(a.g, a.p[f], 2ll * q, (2ll * q + 1) < a.g.ncell, t);
-        } else {
-          const unsigned long long seed = a.seeds[(size_t)a.seed_row[f] * a.n_real + r];
-          const double mu = a.p[f][0], sigma = a.p[f][1];
-#pragma unroll
-          for (int b = 0; b < 3; ++b) {
-            double z0, z1;
-            philox_normal_pair(seed, a.stream[f], 3ull * q + b, z0, z1);
-            t[2 * b] = __dadd_rn(__dmul_rn(z0, sigma), mu);
-            t[2 * b + 1] = __dadd_rn(__dmul_rn(z1, sigma), mu);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) v[k] = first ? t[k] : __dadd_rn(v[k], t[k]);
-        first = false;
-      }
+    if (live) {
+      if (simple) simple_pair(a, seed, q, v);
+      else generic_pair(a, q, r, v);
     }
     const long long c0 = 2ll * q;
-    double* o = out + ((long long)g * a.g.ncell + c0) * (3 * RL) + rl;
-    o[0] = v[0]; o[RL] = v[1]; o[2 * RL] = v[2];
-    if (c0 + 1 < a.g.ncell) { o[3 * RL] = v[3]; o[4 * RL] = v[4]; o[5 * RL] = v[5]; }
+    const bool has2 = c0 + 1 < a.g.ncell;
+    if (RL == 4) {
+      double* o = out + (((long long)g * a.g.ncell + c0) * 4 + rl) * 4;
+      *reinterpret_cast<double4*>(o) = make_double4(v[0], v[1], v[2], 0.0);
+      if (has2) *reinterpret_cast<double4*>(o + 16) = make_double4(v[3], v[4], v[5], 0.0);
+    } else {
+      double* o = out + ((long long)g * a.g.ncell + c0) * (3 * RL) + rl;
+      o[0] = v[0]; o[RL] = v[1]; o[2 * RL] = v[2];
+      if (has2) { o[3 * RL] = v[3]; o[4 * RL] = v[4]; o[5 * RL] = v[5]; }
+    }
   }
 }
 
@@ -572,26 +516,19 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
     const uintptr_t addr = reinterpret_cast<uintptr_t>(outs[type]);
     if (type == 0) {
       const long long row_elems = g.ncell * b_stride;
-      if (b_stride == 16) {
-        // realisation-interleaved: [ceil(rows/4), ncell, 4, 4]; only meaningful per realisation
-        if (need != n_real || addr % 32 != 0) return IMB_EINVAL;
-        if (g.ncell >= (1ll << 30)) return IMB_EUNSUPPORTED;   // 32-bit pair index
-        const int n_groups = (need + 3) / 4;
-        const long long work4 = ((g.ncell + 1) / 2) * 4;
-        int bx = grid_blocks(work4, 256, 8) / n_groups;
-        if (bx < 1) bx = 1;
-        field_b_il4_kernel<<<dim3(bx, n_groups), 256, 0, stream>>>(a, outs[type]);
-      } else if (b_stride == 24 || b_stride == 48 || b_stride == 96) {
-        // wide interleave: [ceil(rows/RL), ncell, 3, RL]
-        const int rl = b_stride / 3;
+      if (b_stride >= 16) {
+        // realisation-interleaved layouts (see field_b_il_kernel); only meaningful per realisation
+        const int rl = b_stride == 16 ? 4 : b_stride / 3;
         if (need != n_real || addr % 32 != 0) return IMB_EINVAL;
         if ((g.ncell + 1) / 2 * rl >= (1ll << 32)) return IMB_EUNSUPPORTED;   // 32-bit work index
         const int n_groups = (need + rl - 1) / rl;
         int bx = grid_blocks(((g.ncell + 1) / 2) * rl, 256, 8) / n_groups;
         if (bx < 1) bx = 1;
-        if (rl == 32) field_b_rl_kernel<32><<<dim3(bx, n_groups), 256, 0, stream>>>(a, outs[type]);
-        else if (rl == 16) field_b_rl_kernel<16><<<dim3(bx, n_groups), 256, 0, stream>>>(a, outs[type]);
-        else field_b_rl_kernel<8><<<dim3(bx, n_groups), 256, 0, stream>>>(a, outs[type]);
+        const dim3 grid(bx, n_groups);
+        if (rl == 4) field_b_il_kernel<4><<<grid, 256, 0, stream>>>(a, outs[type]);
+        else if (rl == 32) field_b_il_kernel<32><<<grid, 256, 0, stream>>>(a, outs[type]);
+        else if (rl == 16) field_b_il_kernel<16><<<grid, 256, 0, stream>>>(a, outs[type]);
+        else field_b_il_kernel<8><<<grid, 256, 0, stream>>>(a, outs[type]);
       } else if (b_stride == 3) {
         const bool vec = (addr % 16 == 0) && (need == 1 || row_elems % 2 == 0);
         if (vec) field_b_kernel<3, true><<<blocks, 256, 0, stream>>>(a, outs[type]);
