@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
   const long long oy = sy * CS, ox = sx * CS;
   const double* __restrict__ Bg = a.B + (long long)g * a.g.ncell * CS + rl;
 
+  const double two_lam2 = 2.0 * a.lam2;
   double dm_geo = 0.0;                         // shared-n_e dispersion measure of this lane's steps
   double carry = 0.0, dm = 0.0, I = 0.0, Q = 0.0, U = 0.0;
 
@@ -123,16 +124,22 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
         }
       }
       if (ne_shared) dm_geo += ne_s * a.dl_pc;
-      RlGeo& ge = s_geo[warp][lane];
-      ge.tx = c.tx; ge.ty = c.ty; ge.tz = c.tz; ge.ne = ne_s; ge.cre = cre_s;
-      ge.base = inside ? (int)c.base : -1;
+      double kp = a.sync_k;
       if (HAS_CRE && VAR_P) {
         const double R = sqrt(px * px + py * py);
         const double p = a.alpha - a.beta * R - a.theta * pz;
-        s_var[warp][lane][0] = inside ? sync_coeff_var(a, p) : 0.0;
+        kp = inside ? sync_coeff_var(a, p) : 0.0;
+        s_var[warp][lane][0] = kp;
         s_var[warp][lane][1] = (p + 1.0) / (p + 7.0 / 3.0);
         s_var[warp][lane][2] = (p + 1.0) * 0.25;
       }
+      // the realisation-independent leading factors are folded in here, in the oracle's order:
+      // 0.812 n_e (Faraday) and CRE K(p) [dl] (emissivity)
+      RlGeo& ge = s_geo[warp][lane];
+      ge.tx = c.tx; ge.ty = c.ty; ge.tz = c.tz;
+      ge.ne = __dmul_rn(0.812, ne_s);
+      ge.cre = P3 ? cre_s * kp * a.dl_cm : cre_s * kp;
+      ge.base = inside ? (int)c.base : -1;
     }
     __syncwarp();
 
@@ -189,23 +196,28 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
       }
       double phi = 0.0;
       if (HAS_NE) {
-        double ne_s = g1.y;
+        double ne812 = g1.y;                               // 0.812 n_e
         if (!ne_shared) {
-          ne_s = live ? interp_scalar(a.ne + a.ne_row * rr, c) : 0.0;
+          const double ne_s = live ? interp_scalar(a.ne + a.ne_row * rr, c) : 0.0;
           dm += ne_s * a.dl_pc;
+          ne812 = __dmul_rn(0.812, ne_s);
         }
         const double2* pp = reinterpret_cast<const double2*>(&pc);
         const double2 n01 = pp[0], n2h = pp[1];
         const double bpar = -(bx * n01.x + by * n01.y + bz * n2h.x);
-        const double f = __dmul_rn(__dmul_rn(__dmul_rn(0.812, ne_s), bpar), a.dl_pc);
+        const double f = __dmul_rn(__dmul_rn(ne812, bpar), a.dl_pc);
         phi = carry + 0.5 * f;
         carry += f;
       }
       if (HAS_CRE) {
-        double cre_s = g2.x;
-        if (!cre_shared) cre_s = live ? interp_scalar(a.cre + a.cre_row * rr, c) : 0.0;
-        double kp = a.sync_k, pif = a.pol_frac, expo = a.expo;
-        if (VAR_P) { kp = s_var[warp][sl][0]; pif = s_var[warp][sl][1]; expo = s_var[warp][sl][2]; }
+        double pif = a.pol_frac, expo = a.expo;
+        if (VAR_P) { pif = s_var[warp][sl][1]; expo = s_var[warp][sl][2]; }
+        double ck = g2.x;                                  // CRE K(p) dl (P3) or CRE K(p)
+        if (!cre_shared) {
+          const double cre_s = live ? interp_scalar(a.cre + a.cre_row * rr, c) : 0.0;
+          const double kp = VAR_P ? s_var[warp][sl][0] : a.sync_k;
+          ck = P3 ? cre_s * kp * a.dl_cm : cre_s * kp;
+        }
         const double2* pp = reinterpret_cast<const double2*>(&pc);
         const double2 h0 = pp[1], h12 = pp[2], e01 = pp[3];          // (n2, north0) (north1, north2) east
         const double bn = bx * h0.y + by * h12.x + bz * h12.y;
@@ -214,13 +226,12 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
         if (bp2 > 0.0) {
           double em, qc, uc;
           if (P3) {                                  // (p+1)/4 == 1: no pow, no division
-            const double ck = cre_s * kp * a.dl_cm;
             em = ck * bp2;
             const double gq = -ck * pif;
             qc = gq * (bn2 - be2);
             uc = gq * (2.0 * bn * be);
           } else {
-            em = cre_s * kp * pow(bp2, expo) * a.dl_cm;
+            em = ck * pow(bp2, expo) * a.dl_cm;
             const double gq = -em * pif / bp2;
             qc = gq * (bn2 - be2);
             uc = gq * (2.0 * bn * be);
@@ -228,9 +239,9 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
           I += em;
           if (HAS_NE) {
             double sa, ca;
-            sincos_cw(2.0 * phi * a.lam2, sa, ca);
-            Q += qc * ca - uc * sa;
-            U += qc * sa + uc * ca;
+            sincos_cw(phi * two_lam2, sa, ca);              // == 2 phi lam2 exactly
+            Q = fma(qc, ca, fma(-uc, sa, Q));
+            U = fma(qc, sa, fma(uc, ca, U));
           } else {
             Q += qc;
             U += uc;
