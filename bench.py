@@ -385,11 +385,17 @@ def main():
             'clocks': clocks,
             'roofline': {'kernel': 'los_il4s_kernel' if ev.b_stride == 16 else 'los_rl_kernel', 'bound': 'hbm', 'achieved': los_gbs, 'peak': peak,
                          'unit': 'GB/s', 'frac': los_gbs / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full,
-                         # profiles/r01_ncu_full_final.csv (c3, 1 GPU only)
-                         'traffic': 3914488000 if (args.workload == 'c3' and world == 1) else None,
-                         'limiter': 'L1 data-pipe wavefronts of the trilinear gathers (86 % of peak); '
-                                    'the padded B grid leaves HBM once (DRAM 8 % busy)',
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full:
+                         # profiles/r01_ncu_full_v7.csv (los_rl_kernel) / r01_ncu_full_final.csv
+                         # (los_il4s_kernel); c3 on 1 GPU only
+                         'traffic': ((2910590000 if ev.b_stride == 96 else 3914488000 if ev.b_stride == 16 else None)
+                                     if (args.workload == 'c3' and world == 1) else None),
+                         'limiter': ('not HBM at this size: L1 data pipe 72 % busy (48 wavefronts of corner loads '
+                                     '+ 28 of shared-memory broadcasts per step), 45 % of stall samples wait on '
+                                     'the corner gathers; the B grid leaves HBM once (DRAM 12 % busy)'
+                                     if ev.b_stride != 16 else
+                                     'L1 data-pipe wavefronts of the trilinear gathers (86 % of peak); '
+                                     'the padded B grid leaves HBM once (DRAM 8 % busy)'),
                          'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)',
                          'algorithmic_bytes_per_launch': int(los_bytes),
                          'ms_per_launch': stage[1]},
