@@ -54,3 +54,26 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Grid) == 64
     assert C.sizeof(_lib.FieldDesc) == 80
     assert C.sizeof(_lib.LosCfg) == 232
+
+
+def test_field_layout_selection_host_only(lib):
+    """engine.pick_b_stride / b_shape / b_stride_of / field_shapes: the layout follows the shard size."""
+    import torch
+    from imagine_b200 import engine
+
+    class G:                      # field_shapes only reads ncell
+        ncell = 10
+    assert [engine.pick_b_stride(n) for n in (256, 64, 32, 48, 16, 8, 24, 12, 4, 1)] == \
+        [96, 96, 96, 48, 48, 24, 24, 16, 16, 16]
+    for bs, rows in ((96, 64), (96, 33), (48, 16), (24, 8), (16, 5), (4, 3), (3, 3)):
+        shape = engine.b_shape(rows, G.ncell, bs)
+        assert engine.b_stride_of(torch.empty(shape, dtype=torch.float64)) == bs
+        rl = {96: 32, 48: 16, 24: 8, 16: 4}.get(bs)
+        if rl:                    # whole groups: lanes beyond `rows` exist and are zero-filled by the kernel
+            assert shape[0] * rl >= rows and (shape[0] - 1) * rl < rows
+    stochastic = [(_lib.FIELD_CONST_B, [0, 1, 0], 0), (_lib.FIELD_GAUSS_B, [0, 2], 1), (_lib.FIELD_EXP_NE, [.01, 3, .1], 2)]
+    shapes, bs = engine.field_shapes(G, stochastic, 32, 'auto')
+    assert bs == 96 and shapes['magnetic_field'] == (1, 10, 3, 32) and shapes['thermal_electron_density'] == (1, 10)
+    # interleaving needs one B row per realisation: a deterministic B falls back to the padded rows
+    shapes, bs = engine.field_shapes(G, stochastic[:1] + stochastic[2:], 32, 'auto')
+    assert bs == 4 and shapes['magnetic_field'] == (1, 10, 4)
