@@ -19,7 +19,8 @@
 //     is linear in Q+iU).
 // Measured and dropped: an L1 prefetch (CCTL.PF1, one line per lane) of the next in-box step's corner
 // lines -- 4.24 vs 3.47 ms; the prefetch requests cost more LSU time than the latency they hide.
-// 128-thread blocks at 72 registers (28 instead of 24 warps / SM): 3.58 vs 3.47 ms.
+// 128-thread blocks at 72 registers (28 instead of 24 warps / SM): 3.58 vs 3.47 ms.  Two realisation
+// groups per warp (geometry and broadcasts shared, half the warps): 3.88-4.24 vs 3.48 ms.
 // Numeric definition: oracle/los.py.
 #include <cstdlib>
 #include "los.cuh"
