@@ -22,7 +22,10 @@
 namespace imb {
 
 constexpr int KMAX = 16;           // observables per batch launch
-constexpr int GCOLS = 256;         // columns per Gram slice (fixed => summation order depends on m only)
+// columns per Gram slice: fixed, so the summation order depends on m only (batching never changes a
+// key's value); 192 fills 148 SMs x 3 CTAs in 2.9 waves at C3 (5 keys x 256 slices), 256 left a third wave
+// that was 16 % full
+constexpr int GCOLS = 192;
 
 struct RowLayout {
   int rpb;                 // rows per block
