@@ -20,7 +20,9 @@
 // Measured and dropped: an L1 prefetch (CCTL.PF1, one line per lane) of the next in-box step's corner
 // lines -- 4.24 vs 3.47 ms; the prefetch requests cost more LSU time than the latency they hide.
 // 128-thread blocks at 72 registers (28 instead of 24 warps / SM): 3.58 vs 3.47 ms.  Two realisation
-// groups per warp (geometry and broadcasts shared, half the warps): 3.88-4.24 vs 3.48 ms.
+// groups per warp (geometry and broadcasts shared, half the warps): 3.88-4.24 vs 3.48 ms.  Not built:
+// reusing the 24 corner values when the next step stays in the same cell (32 % of the steps at C3)
+// needs ~120 registers (280 bytes of spills at 80), i.e. 16 instead of 24 warps / SM.
 // Numeric definition: oracle/los.py.
 #include <cstdlib>
 #include "los.cuh"
