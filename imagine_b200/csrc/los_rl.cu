@@ -29,8 +29,11 @@
 
 namespace imb {
 
-struct __align__(16) RlPix {   // per warp, in shared memory; n|north|east re-read as four 128-bit words
-  double n[3], north[3], east[2];
+struct __align__(16) RlPix {   // per warp, in shared memory
+  // sky basis by its angles: n = (st cp, st sp, ct), north = (-ct cp, -ct sp, st), east = (-sp, cp, 0);
+  // the march re-reads (st, ct) and (cp, sp) as two 128-bit words per step instead of n|north|east
+  double st, ct, cp, sp;
+  double n[3];
   int j_lo, j_hi;
 };
 
@@ -59,8 +62,7 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
     const double sth = sqrt(nx * nx + ny * ny);
     const double cph = sth > 0.0 ? nx / sth : 1.0, sph = sth > 0.0 ? ny / sth : 0.0;
     pc.n[0] = nx; pc.n[1] = ny; pc.n[2] = nz;
-    pc.east[0] = -sph; pc.east[1] = cph;
-    pc.north[0] = -nz * cph; pc.north[1] = -nz * sph; pc.north[2] = sth;
+    pc.st = sth; pc.ct = nz; pc.cp = cph; pc.sp = sph;
     // conservative in-box step range (the exact in-box test is still done per step)
     double tmin = 0.0, tmax = a.dr * (double)a.n_steps;
     const double nn[3] = {nx, ny, nz};
@@ -196,6 +198,9 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
         x10 = lerp(x10, x11, ty); y10 = lerp(y10, y11, ty); z10 = lerp(z10, z11, ty);
         bx = lerp(x00, x10, tx); by = lerp(y00, y10, tx); bz = lerp(z00, z10, tx);
       }
+      const double2 sc = reinterpret_cast<const double2*>(&pc)[0];   // (sin, cos) of the colatitude
+      const double2 cs = reinterpret_cast<const double2*>(&pc)[1];   // (cos, sin) of the longitude
+      const double bh = bx * cs.x + by * cs.y;                         // horizontal part along the ray's azimuth
       Cell c;
       if ((HAS_NE && !ne_shared) || (HAS_CRE && !cre_shared)) {
         c.base = base; c.sy = sy; c.sx = sx; c.tx = tx; c.ty = ty; c.tz = tz;
@@ -208,9 +213,7 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
           dm += ne_s * a.dl_pc;
           ne812 = __dmul_rn(0.812, ne_s);
         }
-        const double2* pp = reinterpret_cast<const double2*>(&pc);
-        const double2 n01 = pp[0], n2h = pp[1];
-        const double bpar = -(bx * n01.x + by * n01.y + bz * n2h.x);
+        const double bpar = -(sc.x * bh + sc.y * bz);      // -(B . n)
         const double f = __dmul_rn(__dmul_rn(ne812, bpar), a.dl_pc);
         phi = carry + 0.5 * f;
         carry += f;
@@ -224,10 +227,8 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
           const double kp = VAR_P ? s_var[warp][sl][0] : a.sync_k;
           ck = P3 ? cre_s * kp * a.dl_cm : cre_s * kp;
         }
-        const double2* pp = reinterpret_cast<const double2*>(&pc);
-        const double2 h0 = pp[1], h12 = pp[2], e01 = pp[3];          // (n2, north0) (north1, north2) east
-        const double bn = bx * h0.y + by * h12.x + bz * h12.y;
-        const double be = bx * e01.x + by * e01.y;
+        const double bn = sc.x * bz - sc.y * bh;           // B . north
+        const double be = by * cs.x - bx * cs.y;           // B . east
         const double bn2 = bn * bn, be2 = be * be, bp2 = bn2 + be2;
         if (bp2 > 0.0) {
           double em, qc, uc;
