@@ -390,8 +390,8 @@ def main():
                          # (los_il4s_kernel); c3 on 1 GPU only
                          'traffic': ((2910590000 if ev.b_stride == 96 else 3914488000 if ev.b_stride == 16 else None)
                                      if (args.workload == 'c3' and world == 1) else None),
-                         'limiter': ('not HBM at this size: L1 data pipe 72 % busy (48 wavefronts of corner loads '
-                                     '+ 28 of shared-memory broadcasts per step), 45 % of stall samples wait on '
+                         'limiter': ('not HBM at this size: L1 data pipe ~70 % busy (48 wavefronts of corner loads '
+                                     '+ 20 of shared-memory broadcasts per step), 45 % of stall samples wait on '
                                      'the corner gathers; the B grid leaves HBM once (DRAM 12 % busy)'
                                      if ev.b_stride != 16 else
                                      'L1 data-pipe wavefronts of the trilinear gathers (86 % of peak); '
