@@ -42,7 +42,9 @@ struct __align__(16) RlGeo {   // per (warp, step slot): everything realisation-
   int base, pad;               // base < 0: step is outside the box
 };
 
-template <int RL, bool HAS_NE, bool HAS_CRE, bool VAR_P, bool P3, int MINB>
+// SHARED: every scalar grid present (n_e, CRE) is one grid for all realisations -- the usual case;
+// the per-realisation gathers of RandomThermalElectrons are then compiled out of the march
+template <int RL, bool HAS_NE, bool HAS_CRE, bool VAR_P, bool P3, bool SHARED, int MINB>
 __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant__ LosArgs a) {
   constexpr int S = 32 / RL;                 // ray segments marched side by side by one warp
   __shared__ RlPix s_pix[8];
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
   const int j_lo = pc.j_lo, j_hi = pc.j_hi;
   const int seg_len = (j_hi - j_lo + 1 + S - 1) / S;     // <= 0 when the ray misses the box
   const long long sy = a.g.n[2], sx = (long long)a.g.n[1] * a.g.n[2];
-  const bool ne_shared = HAS_NE && a.ne_row == 0, cre_shared = HAS_CRE && a.cre_row == 0;
+  const bool ne_shared = HAS_NE && (SHARED || a.ne_row == 0), cre_shared = HAS_CRE && (SHARED || a.cre_row == 0);
   // corner strides of the wide layout, in doubles
   constexpr long long CS = 3 * RL;
   const long long oy = sy * CS, ox = sx * CS;
@@ -305,9 +307,14 @@ static int launch_rl_variant(const LosArgs& a, cudaStream_t s) {
   // measured at C3 (64 realisations): RL 32 -> 80 registers (3.40 vs 3.69 ms), RL 16 -> 64 (3.84 vs 4.01)
   int minb = RL == 32 ? 3 : 4;
   if (const char* e = getenv("IMB_LOS_MINB")) minb = atoi(e);
-  if (minb >= 4) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, 4><<<grid, 256, 0, s>>>(a);
-  else if (minb == 3) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, 3><<<grid, 256, 0, s>>>(a);
-  else los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, 2><<<grid, 256, 0, s>>>(a);
+  const bool shared = (!HAS_NE || a.ne_row == 0) && (!HAS_CRE || a.cre_row == 0);
+  if (shared) {
+    if (minb >= 4) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, 4><<<grid, 256, 0, s>>>(a);
+    else los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, 3><<<grid, 256, 0, s>>>(a);
+  } else {
+    if (minb >= 4) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, false, 4><<<grid, 256, 0, s>>>(a);
+    else los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, false, 3><<<grid, 256, 0, s>>>(a);
+  }
   return IMB_OK;
 }
 
