@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libimagine_b200.so')
+# IMB_LIB_PATH: A/B runs of tuning builds (tools/build_variant.sh); the product is the in-tree default
+LIB_PATH = os.environ.get('IMB_LIB_PATH') or os.path.join(HERE, 'libimagine_b200.so')
 
 IMB_OK, IMB_EINVAL, IMB_ECUDA, IMB_ENOMEM, IMB_ENOTINIT, IMB_EBOUNDS, IMB_ESINGULAR, IMB_EUNSUPPORTED = range(8)
 

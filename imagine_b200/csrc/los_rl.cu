@@ -1,58 +1,126 @@
 // Stage 2, realisation-lane kernel: line-of-sight integration over the wide realisation-interleaved
 // layout B[group][cell][component][RL] (b_stride 3*RL, RL = 32, 16 or 8 realisations per group).
 //
-// los_il4s_kernel (lane = 4*sample + realisation) is bound by the L1 data pipe (ncu: 84-86 % of
-// the wavefront peak): every 256-bit corner gather costs the 8-wavefront minimum, a quarter of the
-// bytes are padding, the (n_e, CRE) gathers and the shared-memory ray accumulators ride the same
-// pipe.  Here a LANE IS A REALISATION and the warp marches ONE ray sample by sample:
+// A LANE IS A REALISATION and the warp marches ONE ray sample by sample:
 //   * every corner component is one 64-bit load per lane, RL consecutive doubles per request
-//     (256 B = 2 wavefronts at RL 32, no padding): 48 wavefronts per 32 sample-realisations
-//     instead of ~140;
+//     (256 B = 2 L1 wavefronts at RL 32, no padding);
 //   * geometry, the in-box test, the shared n_e / CRE interpolants and the spectral-index terms do
 //     not depend on the realisation: the 32 lanes compute them for 32 consecutive steps at once
 //     (phase A), park them in shared memory, and the march (phase B) re-reads them as broadcasts;
-//     only in-box steps are marched (ballot mask);
-//   * the ray accumulators (Faraday depth, I, Q, U) are plain registers: no scan, no shuffles, no
-//     shared-memory read-modify-write in the loop;
+//   * THE CELL STAYS RESIDENT IN REGISTERS.  The first version of this kernel re-fetched all 24
+//     corner values every step and was bound by the L1 data pipe (ncu r01: 65 GB through L1 for
+//     3.4 GB of field, 72 % of the wavefront peak).  At C3 32 % of the in-box steps stay in the cell
+//     of the previous step and 47 % cross exactly one face.  The 8 vertices live in 8 register slots
+//     addressed by the PARITY of the vertex index per axis (vertex (X,Y,Z) -> slot (X&1, Y&1, Z&1)),
+//     so a vertex never moves between slots while the ray walks: crossing a face replaces the four
+//     slots of the face left behind and nothing is shuffled.  The lerp always runs slot 0 -> slot 1
+//     with t' = t for an even cell index and 1 - t for an odd one (computed in phase A).  Which slots
+//     to (re)load is a warp-uniform 8-bit mask from phase A; the loads are predicated, not branched,
+//     and the loads of step k+1 are issued between the interpolation and the physics of step k.
+//     Average corner loads per step at C3: 24 -> 9.8.
+//   * the ray accumulators (Faraday depth, I, Q, U) are plain registers; the Faraday depth is carried
+//     pre-multiplied by 2 lambda^2 (the rotation angle), -Pi(p) is applied once after the march, and
+//     the rotation uses short Taylor kernels whenever the whole warp's angle is below 1/8 rad;
 //   * RL = 16 / 8: the 2 / 4 lane groups march consecutive segments of the ray; when the segments are
 //     joined, each outer one is rotated by the total Faraday depth of those inside it (the rotation
 //     is linear in Q+iU).
-// Measured and dropped: an L1 prefetch (CCTL.PF1, one line per lane) of the next in-box step's corner
-// lines -- 4.24 vs 3.47 ms; the prefetch requests cost more LSU time than the latency they hide.
-// 128-thread blocks at 72 registers (28 instead of 24 warps / SM): 3.58 vs 3.47 ms.  Two realisation
-// groups per warp (geometry and broadcasts shared, half the warps): 3.88-4.24 vs 3.48 ms.  Not built:
-// reusing the 24 corner values when the next step stays in the same cell (32 % of the steps at C3)
-// needs ~120 registers (280 bytes of spills at 80), i.e. 16 instead of 24 warps / SM.
+// Measured and dropped (first version): an L1 prefetch (CCTL.PF1) of the next step's corner lines
+// (4.24 vs 3.47 ms); 128-thread blocks at 72 registers (3.58 vs 3.47 ms); two realisation groups per
+// warp (3.88-4.24 vs 3.48 ms).
 // Numeric definition: oracle/los.py.
 #include <cstdlib>
 #include "los.cuh"
 
+// block shape: warps (= pixels) per block and resident blocks per SM the register budget is cut for
+#ifndef IMB_LOS_WPB
+#define IMB_LOS_WPB 4
+#endif
+#ifndef IMB_LOS_MINB
+#define IMB_LOS_MINB 4
+#endif
+
 namespace imb {
 
 struct __align__(16) RlPix {   // per warp, in shared memory
-  // sky basis by its angles: n = (st cp, st sp, ct), north = (-ct cp, -ct sp, st), east = (-sp, cp, 0);
-  // the march re-reads (st, ct) and (cp, sp) as two 128-bit words per step instead of n|north|east
+  // sky basis by its angles: n = (st cp, st sp, ct), north = (-ct cp, -ct sp, st), east = (-sp, cp, 0)
   double st, ct, cp, sp;
   double n[3];
   int j_lo, j_hi;
 };
 
 struct __align__(16) RlGeo {   // per (warp, step slot): everything realisation-independent
-  double tx, ty, tz, ne, cre;
-  int base, pad;               // base < 0: step is outside the box
+  double w[8];                 // trilinear weight of each vertex slot
+  double ne, cre;              // 0.812 n_e dl [2 lambda^2]; CRE K(p) [dl]
+  int base;                    // cell index of the slot-(0,0,0) vertex (the all-even one)
+  int code;                    // bits 0-7: slots to load (bit 4 sx + 2 sy + sz); 8-10: parity of ix, iy, iz;
+  int pad[2];                  // bit 11: step is inside the box
 };
+
+// three predicated 64-bit loads (the x, y, z components of one vertex slot) in program order
+template <int RL>
+__device__ __forceinline__ void load_slot(double& x, double& y, double& z, const double* p, int flag) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t"
+      "@q ld.global.nc.f64 %0, [%4];\n\t"
+      "@q ld.global.nc.f64 %1, [%4+%5];\n\t"
+      "@q ld.global.nc.f64 %2, [%4+%6];\n\t}"
+      : "+d"(x), "+d"(y), "+d"(z)
+      : "r"(flag), "l"(p), "n"(RL * 8), "n"(RL * 16));
+}
+
+// shared-memory reads by 32-bit address, volatile: they stay where the march puts them (ahead of the
+// arithmetic they feed, so one latency is exposed per step instead of one per use)
+template <int OFF>
+__device__ __forceinline__ double2 lds_d2(unsigned int addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ int2 lds_i2(unsigned int addr) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0,%1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(OFF));
+  return v;
+}
+
+// kernel parameters: the LOS arguments plus the Taylor coefficients of the small-angle rotation as
+// constant-bank operands (a __constant__ array costs one LDC per coefficient and step)
+struct RlArgs {
+  LosArgs a;
+  double ts[4], tc[5];
+  int sx, sy;          // cell strides of the x and y axes (launch_los_rl guarantees ncell < 2^31)
+};
+
+// sin and cos for |x| <= 1/8: Taylor to x^9 / x^10 (truncation below 3e-17 relative).  Horner form: every
+// FMA takes its coefficient straight from the constant bank (the Estrin form needs two per FMA, i.e. an
+// LDC and a register each)
+__device__ __forceinline__ void sincos_small(const RlArgs& ra, double x, double& sn, double& cs) {
+  const double z = x * x;
+  double ps = fma(ra.ts[3], z, ra.ts[2]), pc = fma(ra.tc[4], z, ra.tc[3]);
+  ps = fma(ps, z, ra.ts[1]); pc = fma(pc, z, ra.tc[2]);
+  ps = fma(ps, z, ra.ts[0]); pc = fma(pc, z, ra.tc[1]);
+  pc = fma(pc, z, ra.tc[0]);
+  sn = fma(x * z, ps, x);
+  cs = fma(z, pc, 1.0);
+}
 
 // SHARED: every scalar grid present (n_e, CRE) is one grid for all realisations -- the usual case;
 // the per-realisation gathers of RandomThermalElectrons are then compiled out of the march
-template <int RL, bool HAS_NE, bool HAS_CRE, bool VAR_P, bool P3, bool SHARED, int MINB>
-__global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant__ LosArgs a) {
+template <int RL, bool HAS_NE, bool HAS_CRE, bool VAR_P, bool P3, bool SHARED, int WPB, int MINB>
+__global__ void __launch_bounds__(32 * WPB, MINB) los_rl_kernel(const __grid_constant__ RlArgs ra) {
+  const LosArgs& a = ra.a;
   constexpr int S = 32 / RL;                 // ray segments marched side by side by one warp
-  __shared__ RlPix s_pix[8];
-  __shared__ RlGeo s_geo[8][32];
-  __shared__ double s_var[VAR_P ? 8 : 1][32][3];
+  constexpr unsigned int FULL = 0xffffffffu;
+  constexpr unsigned int GEO = sizeof(RlGeo);
+  static_assert(sizeof(RlGeo) == 96, "RlGeo layout is addressed by byte offsets below");
+  __shared__ RlPix s_pix[WPB];
+  __shared__ RlGeo s_geo[WPB * 32 + 1];      // + 1: the march reads one step slot ahead
+  __shared__ double s_var[VAR_P ? WPB : 1][32][3];
+  __shared__ double s_dm[WPB][32];           // shared-n_e dispersion measure of each lane's steps
+  __shared__ int4 s_last[WPB][S];            // cell of the step before this chunk, per segment (w: in box)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int seg = lane / RL, rl = lane % RL;
-  const int pix = blockIdx.x * 8 + warp;
+  const int pix = blockIdx.x * WPB + warp;
   if (pix >= a.m) return;                               // whole warp exits together
   const int g = blockIdx.y;
   const int rr = g * RL + rl;
@@ -88,24 +156,31 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
   }
   __syncwarp();
 
-  const int j_lo = pc.j_lo, j_hi = pc.j_hi;
-  const int seg_len = (j_hi - j_lo + 1 + S - 1) / S;     // <= 0 when the ray misses the box
-  const long long sy = a.g.n[2], sx = (long long)a.g.n[1] * a.g.n[2];
+  const int seg_len = (pc.j_hi - pc.j_lo + 1 + S - 1) / S;     // <= 0 when the ray misses the box
+  const int sy = ra.sy, sx = ra.sx;
   const bool ne_shared = HAS_NE && (SHARED || a.ne_row == 0), cre_shared = HAS_CRE && (SHARED || a.cre_row == 0);
-  // corner strides of the wide layout, in doubles
-  constexpr long long CS = 3 * RL;
-  const long long oy = sy * CS, ox = sx * CS;
+  constexpr long long CS = 3 * RL;                       // doubles per vertex of the wide layout
   const double* __restrict__ Bg = a.B + (long long)g * a.g.ncell * CS + rl;
+  // shared-memory byte address of this lane group's first step slot
+  unsigned int geo_seg = (unsigned int)__cvta_generic_to_shared(&s_geo[warp * 32 + seg * RL]);
 
-  const double two_lam2 = 2.0 * a.lam2;
-  double dm_geo = 0.0;                         // shared-n_e dispersion measure of this lane's steps
+  // the Faraday depth is carried as the rotation angle 2 lambda^2 phi when it rotates anything
+  const double st = pc.st, ct = pc.ct, cp = pc.cp, sp = pc.sp;
+  s_dm[warp][lane] = 0.0;
+  if (rl == RL - 1) s_last[warp][seg] = make_int4(0, 0, 0, 0);
+  __syncwarp();
   double carry = 0.0, dm = 0.0, I = 0.0, Q = 0.0, U = 0.0;
+  // the resident cell: v[slot][component], slot = 4 (X&1) + 2 (Y&1) + (Z&1)
+  double v[8][3];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) v[s][0] = v[s][1] = v[s][2] = 0.0;
 
   for (int cb = 0; cb < seg_len; cb += RL) {
     // ---- phase A: lane (seg, rl) prepares step j of its segment --------------------------------
     {
       const int off = cb + rl;
-      const int j = j_lo + seg * seg_len + off;
+      const int j_hi = pc.j_hi;
+      const int j = pc.j_lo + seg * seg_len + off;
       // geometry: bit-identical to oracle/los.py:sample_geometry (no fma on this path)
       const double r = __dmul_rn((double)j + 0.5, a.dr);
       const double px = __dadd_rn(a.obs[0], __dmul_rn(r, pc.n[0]));
@@ -133,7 +208,7 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
           if (cre_shared) cre_s = interp_scalar(a.cre, c);
         }
       }
-      if (ne_shared) dm_geo += ne_s * a.dl_pc;
+      if (ne_shared) s_dm[warp][lane] += ne_s * a.dl_pc;
       double kp = a.sync_k;
       if (HAS_CRE && VAR_P) {
         const double R = sqrt(px * px + py * py);
@@ -143,21 +218,51 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
         s_var[warp][lane][1] = (p + 1.0) / (p + 7.0 / 3.0);
         s_var[warp][lane][2] = (p + 1.0) * 0.25;
       }
-      // the realisation-independent leading factors are folded in here, in the oracle's order:
-      // 0.812 n_e (Faraday) and CRE K(p) [dl] (emissivity)
-      RlGeo& ge = s_geo[warp][lane];
-      ge.tx = c.tx; ge.ty = c.ty; ge.tz = c.tz;
-      ge.ne = __dmul_rn(0.812, ne_s);
+      // which slots hold a different vertex than after the previous step of this segment
+      int pix_ = __shfl_up_sync(FULL, ix, 1), piy_ = __shfl_up_sync(FULL, iy, 1),
+          piz_ = __shfl_up_sync(FULL, iz, 1), pin_ = __shfl_up_sync(FULL, (int)inside, 1);
+      if (rl == 0) { const int4 l = s_last[warp][seg]; pix_ = l.x; piy_ = l.y; piz_ = l.z; pin_ = l.w; }
+      __syncwarp();
+      if (rl == RL - 1) s_last[warp][seg] = make_int4(ix, iy, iz, (int)inside);
+      const int qx = ix & 1, qy = iy & 1, qz = iz & 1;
+      int code = 0;
+      if (inside) {
+        int cx = 3, cy = 3, cz = 3;                        // bit s: the vertex of parity s changed
+        if (pin_) {
+          cx = (ix + qx != pix_ + (pix_ & 1) ? 1 : 0) | (ix + 1 - qx != pix_ + 1 - (pix_ & 1) ? 2 : 0);
+          cy = (iy + qy != piy_ + (piy_ & 1) ? 1 : 0) | (iy + 1 - qy != piy_ + 1 - (piy_ & 1) ? 2 : 0);
+          cz = (iz + qz != piz_ + (piz_ & 1) ? 1 : 0) | (iz + 1 - qz != piz_ + 1 - (piz_ & 1) ? 2 : 0);
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (((cx >> (s >> 2)) | (cy >> ((s >> 1) & 1)) | (cz >> (s & 1))) & 1) code |= 1 << s;
+        code |= (qx << 8) | (qy << 9) | (qz << 10) | (1 << 11);
+      }
+      // the slot of parity s along an axis holds the vertex i (weight 1 - t) when s == i & 1, else i + 1 (t)
+      RlGeo& ge = s_geo[warp * 32 + lane];
+      const double wx[2] = {qx ? c.tx : 1.0 - c.tx, qx ? 1.0 - c.tx : c.tx};
+      const double wy[2] = {qy ? c.ty : 1.0 - c.ty, qy ? 1.0 - c.ty : c.ty};
+      const double wz[2] = {qz ? c.tz : 1.0 - c.tz, qz ? 1.0 - c.tz : c.tz};
+#pragma unroll
+      for (int s = 0; s < 8; ++s) ge.w[s] = wx[s >> 2] * wy[(s >> 1) & 1] * wz[s & 1];
+      const double dlf = a.dl_pc * ((HAS_NE && HAS_CRE) ? 2.0 * a.lam2 : 1.0);
+      // the realisation-independent leading factors are folded in here:
+      // -0.812 n_e dl [2 lambda^2] (Faraday; the sign of B_par = -B.n rides along) and CRE K(p) [dl]
+      ge.ne = -(__dmul_rn(0.812, ne_s) * dlf);
       ge.cre = P3 ? cre_s * kp * a.dl_cm : cre_s * kp;
-      ge.base = inside ? (int)c.base : -1;
+      ge.base = (int)c.base + qx * sx + qy * sy + qz;
+      ge.code = code;
     }
     __syncwarp();
 
     // ---- phase B: march the in-box steps of this chunk, one realisation per lane ----------------
+    // Software pipeline: the physics of step k-1 and the interpolation of step k are independent, so
+    // they sit in ONE basic block and the scheduler interleaves them (DFMA latency 8.3 clk, 4 warps
+    // per scheduler: a single dependent chain per warp leaves the FP64 pipe half idle); the loads of
+    // step k+1 are issued as soon as step k's interpolation has consumed the slots.
     unsigned int todo = 0;
     {
-      const RlGeo& mine = s_geo[warp][lane];
-      const unsigned int mask = __ballot_sync(0xffffffffu, mine.base >= 0);
+      const unsigned int mask = __ballot_sync(FULL, (s_geo[warp * 32 + lane].code >> 11) & 1);
       if (S == 1) {
         todo = mask;
       } else {
@@ -165,90 +270,116 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
         for (int q = 0; q < S; ++q) todo |= (mask >> (q * RL)) & ((RL < 32 ? (1u << RL) : 0u) - 1u);
       }
     }
-    for (; todo; todo &= todo - 1) {
-      const int sl = seg * RL + (__ffs(todo) - 1);
-      // three 128-bit broadcast reads: (tx, ty) (tz, n_e) (CRE, base)
-      const double2* gp = reinterpret_cast<const double2*>(&s_geo[warp][sl]);
-      const double2 g2 = gp[2];
-      const int base = __double2loint(g2.y);
-      if (S > 1 && base < 0) continue;                  // the other segment's step, not mine
-      const double2 g0 = gp[0], g1 = gp[1];
-      const double tx = g0.x, ty = g0.y, tz = g1.x;
-      const double* p = Bg + (long long)base * CS;
-      double bx, by, bz;
-      {
-        // all 24 corner loads are issued before the first lerp: one exposed memory round trip per
-        // step instead of one per z-pair (ncu source page: the stall samples sat on the first use
-        // after each group of six loads)
-        const double* q1 = p + oy;
-        const double* q2 = p + ox;
-        const double* q3 = q2 + oy;
-        double v0[6], v1[6], v2[6], v3[6];
+    if (todo) {
+      // the in-box steps of a ray are contiguous (the box is convex): march first .. last; a step in
+      // between that no segment has in the box carries zero factors and an empty load mask
+      const int first = __ffs(todo) - 1;
+      int n_left = (31 - __clz(todo)) - first;               // steps after the current one
+      int sl = seg * RL + first;                              // step slot within the warp (VAR_P)
+      unsigned int ga = geo_seg + (unsigned int)first * GEO;  // shared address of the current RlGeo
+      // (re)load the slots whose vertex changed; S == 1: the mask is warp-uniform, skip all when empty
+      auto fetch = [&](const int2 bc) {
+        const int base = bc.x, code = bc.y;
+        if (S == 1 && (code & 0xff) == 0) return;
+#ifdef IMB_LOS_DBG_NOLOAD
+        if (base >= 0) return;
+#endif
+        const int dx = (code & 0x100) ? -sx : sx, dy = (code & 0x200) ? -sy : sy, dz = (code & 0x400) ? -1 : 1;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) v0[k] = ldg64(p + (k / 3) * CS + (k % 3) * RL);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) v1[k] = ldg64(q1 + (k / 3) * CS + (k % 3) * RL);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) v2[k] = ldg64(q2 + (k / 3) * CS + (k % 3) * RL);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) v3[k] = ldg64(q3 + (k / 3) * CS + (k % 3) * RL);
-        double x00 = lerp(v0[0], v0[3], tz), y00 = lerp(v0[1], v0[4], tz), z00 = lerp(v0[2], v0[5], tz);
-        const double x01 = lerp(v1[0], v1[3], tz), y01 = lerp(v1[1], v1[4], tz), z01 = lerp(v1[2], v1[5], tz);
-        x00 = lerp(x00, x01, ty); y00 = lerp(y00, y01, ty); z00 = lerp(z00, z01, ty);
-        double x10 = lerp(v2[0], v2[3], tz), y10 = lerp(v2[1], v2[4], tz), z10 = lerp(v2[2], v2[5], tz);
-        const double x11 = lerp(v3[0], v3[3], tz), y11 = lerp(v3[1], v3[4], tz), z11 = lerp(v3[2], v3[5], tz);
-        x10 = lerp(x10, x11, ty); y10 = lerp(y10, y11, ty); z10 = lerp(z10, z11, ty);
-        bx = lerp(x00, x10, tx); by = lerp(y00, y10, tx); bz = lerp(z00, z10, tx);
-      }
-      const double2 sc = reinterpret_cast<const double2*>(&pc)[0];   // (sin, cos) of the colatitude
-      const double2 cs = reinterpret_cast<const double2*>(&pc)[1];   // (cos, sin) of the longitude
-      const double bh = bx * cs.x + by * cs.y;                         // horizontal part along the ray's azimuth
-      Cell c;
-      if ((HAS_NE && !ne_shared) || (HAS_CRE && !cre_shared)) {
-        c.base = base; c.sy = sy; c.sx = sx; c.tx = tx; c.ty = ty; c.tz = tz;
-      }
-      double phi = 0.0;
-      if (HAS_NE) {
-        double ne812 = g1.y;                               // 0.812 n_e
-        if (!ne_shared) {
-          const double ne_s = live ? interp_scalar(a.ne + a.ne_row * rr, c) : 0.0;
-          dm += ne_s * a.dl_pc;
-          ne812 = __dmul_rn(0.812, ne_s);
+        for (int s = 0; s < 8; ++s) {
+          const int idx = base + ((s & 4) ? dx : 0) + ((s & 2) ? dy : 0) + ((s & 1) ? dz : 0);
+          load_slot<RL>(v[s][0], v[s][1], v[s][2], Bg + (long long)idx * CS, code & (1 << s));
         }
-        const double bpar = -(sc.x * bh + sc.y * bz);      // -(B . n)
-        const double f = __dmul_rn(__dmul_rn(ne812, bpar), a.dl_pc);
-        phi = carry + 0.5 * f;
-        carry += f;
-      }
-      if (HAS_CRE) {
-        double pif = a.pol_frac, expo = a.expo;
-        if (VAR_P) { pif = s_var[warp][sl][1]; expo = s_var[warp][sl][2]; }
-        double ck = g2.x;                                  // CRE K(p) dl (P3) or CRE K(p)
-        if (!cre_shared) {
-          const double cre_s = live ? interp_scalar(a.cre + a.cre_row * rr, c) : 0.0;
-          const double kp = VAR_P ? s_var[warp][sl][0] : a.sync_k;
-          ck = P3 ? cre_s * kp * a.dl_cm : cre_s * kp;
+      };
+      // per-realisation scalar grids (RandomThermalElectrons): same slots, same weights
+      auto slot_scalar = [&](const double* f, const int2 bc, const double* w) {
+        const int dx = (bc.y & 0x100) ? -sx : sx, dy = (bc.y & 0x200) ? -sy : sy, dz = (bc.y & 0x400) ? -1 : 1;
+        double acc = 0.0;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          const int idx = bc.x + ((s & 4) ? dx : 0) + ((s & 2) ? dy : 0) + ((s & 1) ? dz : 0);
+          acc = fma(w[s], __ldg(f + idx), acc);
         }
-        const double bn = sc.x * bz - sc.y * bh;           // B . north
-        const double be = by * cs.x - bx * cs.y;           // B . east
-        const double bn2 = bn * bn, be2 = be * be, bp2 = bn2 + be2;
-        if (bp2 > 0.0) {
-          double em, qc, uc;
-          if (P3) {                                  // (p+1)/4 == 1: no pow, no division
-            em = ck * bp2;
-            const double gq = -ck * pif;
-            qc = gq * (bn2 - be2);
-            uc = gq * (2.0 * bn * be);
-          } else {
-            em = ck * pow(bp2, expo) * a.dl_cm;
-            const double gq = -em * pif / bp2;
-            qc = gq * (bn2 - be2);
-            uc = gq * (2.0 * bn * be);
+        return acc;
+      };
+      // what a step hands from its interpolation to its physics
+      struct Samp { double bx, by, bz, nf, ck, ne_r, cre_r; int sl; };
+      // trilinear interpolation of step (ga, bc): one FMA chain per component over the 8 slots
+      auto interp = [&](const int2 bc) {
+        const double2 w01 = lds_d2<0>(ga), w23 = lds_d2<16>(ga), w45 = lds_d2<32>(ga), w67 = lds_d2<48>(ga);
+        const double2 nc = lds_d2<64>(ga);                    // (-0.812 n_e dl [2 lambda^2], CRE K(p) [dl])
+        Samp o;
+        double e[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          e[k] = w01.x * v[0][k];
+          e[k] = fma(w01.y, v[1][k], e[k]);
+          e[k] = fma(w23.x, v[2][k], e[k]);
+          e[k] = fma(w23.y, v[3][k], e[k]);
+          e[k] = fma(w45.x, v[4][k], e[k]);
+          e[k] = fma(w45.y, v[5][k], e[k]);
+          e[k] = fma(w67.x, v[6][k], e[k]);
+          e[k] = fma(w67.y, v[7][k], e[k]);
+        }
+        o.bx = e[0]; o.by = e[1]; o.bz = e[2];
+        o.nf = nc.x; o.ck = nc.y; o.sl = sl;
+        o.ne_r = o.cre_r = 0.0;
+        if ((HAS_NE && !ne_shared) || (HAS_CRE && !cre_shared)) {
+          const bool in_box = live && (S == 1 || ((bc.y >> 11) & 1));    // S > 1: another segment's step
+          const double w[8] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x, w67.y};
+          if (HAS_NE && !ne_shared) o.ne_r = in_box ? slot_scalar(a.ne + a.ne_row * rr, bc, w) : 0.0;
+          if (HAS_CRE && !cre_shared) o.cre_r = in_box ? slot_scalar(a.cre + a.cre_row * rr, bc, w) : 0.0;
+        }
+        return o;
+      };
+      auto physics = [&](const Samp& p) {
+#ifdef IMB_LOS_DBG_NOPHYS
+        I += p.bx + p.by + p.bz;
+        return;
+#endif
+        const double bh = fma(p.bx, cp, p.by * sp);                     // horizontal part along the ray's azimuth
+        double theta = 0.0;
+        if (HAS_NE) {
+          double nf = p.nf;
+          if (!ne_shared) {
+            dm += p.ne_r * a.dl_pc;
+            nf = -(__dmul_rn(0.812, p.ne_r) * (a.dl_pc * ((HAS_NE && HAS_CRE) ? 2.0 * a.lam2 : 1.0)));
           }
-          I += em;
+          const double bn_ray = fma(st, bh, ct * p.bz);      // B . n = -B_par
+          const double f = nf * bn_ray;
+          theta = fma(0.5, f, carry);
+          carry += f;
+        }
+        if (HAS_CRE) {
+          double ck = p.ck;                                  // CRE K(p) dl (P3) or CRE K(p)
+          if (!cre_shared) {
+            const double kp = VAR_P ? s_var[warp][p.sl][0] : a.sync_k;
+            ck = P3 ? p.cre_r * kp * a.dl_cm : p.cre_r * kp;
+          }
+          const double bn = fma(st, p.bz, -(ct * bh));       // B . north
+          const double be = fma(p.by, cp, -(p.bx * sp));     // B . east
+          const double bn2 = bn * bn;
+          const double bp2 = fma(be, be, bn2), dq = fma(-be, be, bn2), du = (bn + bn) * be;
+          // (Q + iU) accumulates em/Bperp^2 (B_N + i B_E)^2 e^{i theta} [Pi(p)]; the sign and a constant
+          // Pi are applied after the march
+          double gq;
+          if (P3) {                                          // (p+1)/4 == 1: no pow, no division
+            I = fma(ck, bp2, I);
+            gq = ck;
+          } else {
+            const double expo = VAR_P ? s_var[warp][p.sl][2] : a.expo;
+            const double em = bp2 > 0.0 ? ck * pow(bp2, expo) * a.dl_cm : 0.0;
+            I += em;
+            gq = bp2 > 0.0 ? em / bp2 : 0.0;
+            if (VAR_P) gq *= s_var[warp][p.sl][1];
+          }
+          const double qc = gq * dq, uc = gq * du;
           if (HAS_NE) {
+            // the short kernels run unconditionally (straight-line code); a warp with any angle above
+            // 1/8 rad redoes the step's rotation with the full-range kernel
             double sa, ca;
-            sincos_cw(phi * two_lam2, sa, ca);              // == 2 phi lam2 exactly
+            sincos_small(ra, theta, sa, ca);
+            if (!__all_sync(FULL, fabs(theta) <= 0.125)) sincos_cw(theta, sa, ca);
             Q = fma(qc, ca, fma(-uc, sa, Q));
             U = fma(qc, sa, fma(uc, ca, U));
           } else {
@@ -256,23 +387,40 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
             U += uc;
           }
         }
+      };
+      int2 bc = lds_i2<80>(ga);                               // (base, code) of the current step
+      fetch(bc);
+      int2 bcn = lds_i2<GEO + 80>(ga);                        // one step ahead
+      Samp prev = interp(bc);
+      while (n_left > 0) {
+        --n_left; ++sl; ga += GEO;
+        fetch(bcn);                          // the slots are free: step k+1's loads fly during the physics
+        bc = bcn;
+        bcn = lds_i2<GEO + 80>(ga);
+        physics(prev);
+        prev = interp(bc);
       }
+      physics(prev);
     }
     __syncwarp();                                        // phase A of the next chunk reuses s_geo
   }
 
+  if (HAS_CRE) {
+    const double pf = VAR_P ? -1.0 : -a.pol_frac;
+    Q *= pf; U *= pf;
+  }
   // ---- join the segments: the outer one starts at the inner one's total Faraday depth ----------
   if (S > 1) {
 #pragma unroll
     for (int o = RL; o < 32; o <<= 1) {
-      const double cu = __shfl_down_sync(0xffffffffu, carry, o);
-      const double du = __shfl_down_sync(0xffffffffu, dm, o);
-      const double iu = __shfl_down_sync(0xffffffffu, I, o);
-      const double qu = __shfl_down_sync(0xffffffffu, Q, o);
-      const double uu = __shfl_down_sync(0xffffffffu, U, o);
+      const double cu = __shfl_down_sync(FULL, carry, o);
+      const double du = __shfl_down_sync(FULL, dm, o);
+      const double iu = __shfl_down_sync(FULL, I, o);
+      const double qu = __shfl_down_sync(FULL, Q, o);
+      const double uu = __shfl_down_sync(FULL, U, o);
       if (HAS_NE && HAS_CRE) {
         double sa, ca;
-        sincos(2.0 * carry * a.lam2, &sa, &ca);
+        sincos(carry, &sa, &ca);                           // carry is already the rotation angle
         Q += qu * ca - uu * sa;
         U += qu * sa + uu * ca;
       } else {
@@ -282,15 +430,16 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
     }
   }
   if (ne_shared) {
+    double dm_geo = s_dm[warp][lane];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) dm_geo += __shfl_xor_sync(0xffffffffu, dm_geo, o);
+    for (int o = 1; o < 32; o <<= 1) dm_geo += __shfl_xor_sync(FULL, dm_geo, o);
     dm = dm_geo;
   }
   if (seg == 0 && live) {
     const long long o = out_index(a, rr, pix);
     if (HAS_NE) {
       if (a.out_dm) a.out_dm[o] = dm;
-      if (a.out_fd) a.out_fd[o] = carry;
+      if (a.out_fd) a.out_fd[o] = (HAS_NE && HAS_CRE) ? carry / (2.0 * a.lam2) : carry;
     }
     if (HAS_CRE) {
       if (a.out_I) a.out_I[o] = I;
@@ -302,19 +451,21 @@ __global__ void __launch_bounds__(256, MINB) los_rl_kernel(const __grid_constant
 
 template <int RL, bool HAS_NE, bool HAS_CRE, bool VAR_P, bool P3>
 static int launch_rl_variant(const LosArgs& a, cudaStream_t s) {
+  constexpr int WPB = IMB_LOS_WPB, MINB = IMB_LOS_MINB;
   const int n_groups = (a.n_real + RL - 1) / RL;
-  dim3 grid((a.m + 7) / 8, n_groups);
-  // measured at C3 (64 realisations): RL 32 -> 80 registers (3.40 vs 3.69 ms), RL 16 -> 64 (3.84 vs 4.01)
-  int minb = RL == 32 ? 3 : 4;
-  if (const char* e = getenv("IMB_LOS_MINB")) minb = atoi(e);
+  dim3 grid((a.m + WPB - 1) / WPB, n_groups);
+  RlArgs ra;
+  ra.a = a;
+  // Taylor coefficients of sin (x^3 .. x^9) and cos (x^2 .. x^10)
+  const double ts[4] = {-1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0};
+  const double tc[5] = {-0.5, 1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0};
+  for (int k = 0; k < 4; ++k) ra.ts[k] = ts[k];
+  for (int k = 0; k < 5; ++k) ra.tc[k] = tc[k];
+  ra.sy = a.g.n[2];
+  ra.sx = a.g.n[1] * a.g.n[2];
   const bool shared = (!HAS_NE || a.ne_row == 0) && (!HAS_CRE || a.cre_row == 0);
-  if (shared) {
-    if (minb >= 4) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, 4><<<grid, 256, 0, s>>>(a);
-    else los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, 3><<<grid, 256, 0, s>>>(a);
-  } else {
-    if (minb >= 4) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, false, 4><<<grid, 256, 0, s>>>(a);
-    else los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, false, 3><<<grid, 256, 0, s>>>(a);
-  }
+  if (shared) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, WPB, MINB><<<grid, 32 * WPB, 0, s>>>(ra);
+  else los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, false, WPB, MINB><<<grid, 32 * WPB, 0, s>>>(ra);
   return IMB_OK;
 }
 
