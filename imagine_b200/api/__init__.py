@@ -1,17 +1,18 @@
 """
 Reference-facing plugin layer: GPU drop-ins for IMAGINE's Field / Simulator / Likelihood API.
 
-Base classes come from the real `imagine` package when it can be imported; otherwise from
-`mirror.py`, which restates the same interface (the reference needs astropy, mpi4py,
-e13tools ... that are not in this image).
+The base classes are the reference's own (`imagine.fields.Field`, `imagine.simulators.Simulator`,
+`imagine.likelihoods.Likelihood`, the Observable dictionaries): `imagine_b200.reference` imports the
+unmodified package, with stand-ins only for third-party modules this image lacks (astropy.units,
+mpi4py, e13tools, plotting / sampler back ends).
 """
-from ._bases import (Field, MagneticField, ThermalElectronDensityField,              # noqa: F401
-                     CosmicRayElectronDensityField, UniformGrid, Observable, Measurements,
-                     Simulations, Covariances, Masks, Simulator, Likelihood, BACKEND)
+from ._bases import (Field, MagneticField, ThermalElectronDensityField, UniformGrid,   # noqa: F401
+                     Observable, Measurements, Simulations, Covariances, Masks, Simulator,
+                     Likelihood, BACKEND)
 
 from . import units                                                                    # noqa: F401
 from .device_observable import DeviceObservable, ShardedDeviceObservable                                        # noqa: F401
-from .fields import (ConstantMagneticField, NaiveGaussianMagneticField, LSAMagneticField,                # noqa: F401
+from .fields import (CosmicRayElectronDensityField, ConstantMagneticField, NaiveGaussianMagneticField, LSAMagneticField,                # noqa: F401
                      ConstantThermalElectrons, ExponentialThermalElectrons,
                      RandomThermalElectrons, CosThermalElectronDensity,
                      AnalyticCosmicRayElectrons, ConstantCosmicRayElectrons)

@@ -23,10 +23,28 @@ import zlib
 import numpy as np
 
 from . import units as u
-from ._bases import (MagneticField, ThermalElectronDensityField, CosmicRayElectronDensityField)
+from ._bases import Field, MagneticField, ThermalElectronDensityField
 from .. import _lib as L
 
 FLUX_UNIT = (u.GeV * u.m ** 2 * u.s * u.sr) ** (-1)
+
+
+class CosmicRayElectronDensityField(Field):
+    """
+    Gridded cosmic-ray electron flux normalisation at the reference energy, [GeV m^2 s sr]^-1.
+    The reference's class of this name is a stub whose constructor raises (base_fields.py:104-113);
+    the TYPE string is the one the Hammurabi wrapper anticipates (hammurabi.py:58-60).
+    """
+    TYPE = 'cosmic_ray_electron_density'
+    UNITS = FLUX_UNIT
+
+    @property
+    def data_description(self):
+        return ['grid_x', 'grid_y', 'grid_z']
+
+    @property
+    def data_shape(self):
+        return tuple(self.grid.shape)
 
 
 def _stream_id(name):

@@ -1,59 +1,67 @@
 // Stage 2, realisation-lane kernel: line-of-sight integration over the wide realisation-interleaved
 // layout B[group][cell][component][RL] (b_stride 3*RL, RL = 32, 16 or 8 realisations per group).
 //
-// A LANE IS A REALISATION and the warp marches ONE ray sample by sample:
+// A BLOCK IS A PIXEL, A WARP IS A REALISATION GROUP, A LANE IS A REALISATION; the warp marches the
+// ray sample by sample:
 //   * every corner component is one 64-bit load per lane, RL consecutive doubles per request
 //     (256 B = 2 L1 wavefronts at RL 32, no padding);
-//   * geometry, the in-box test, the shared n_e / CRE interpolants and the spectral-index terms do
-//     not depend on the realisation: the 32 lanes compute them for 32 consecutive steps at once
-//     (phase A), park them in shared memory, and the march (phase B) re-reads them as broadcasts;
+//   * geometry, the in-box test, the shared n_e / CRE interpolants, the trilinear weights and the
+//     spectral-index terms do not depend on the realisation: the lanes of ALL the block's warps compute
+//     them for 32 G consecutive steps at once (phase A, G = warps per block), park them in shared
+//     memory, and every warp's march (phase B) re-reads them as broadcasts.  One pixel per block also
+//     gives the block scheduler the finest grain: rays differ 7x in length, and a block of several
+//     pixels holds its registers until its longest ray is done (4 pixels per block: 2.31 ms, one:
+//     2.05 ms at C3);
 //   * THE CELL STAYS RESIDENT IN REGISTERS.  The first version of this kernel re-fetched all 24
 //     corner values every step and was bound by the L1 data pipe (ncu r01: 65 GB through L1 for
 //     3.4 GB of field, 72 % of the wavefront peak).  At C3 32 % of the in-box steps stay in the cell
 //     of the previous step and 47 % cross exactly one face.  The 8 vertices live in 8 register slots
 //     addressed by the PARITY of the vertex index per axis (vertex (X,Y,Z) -> slot (X&1, Y&1, Z&1)),
 //     so a vertex never moves between slots while the ray walks: crossing a face replaces the four
-//     slots of the face left behind and nothing is shuffled.  The lerp always runs slot 0 -> slot 1
-//     with t' = t for an even cell index and 1 - t for an odd one (computed in phase A).  Which slots
-//     to (re)load is a warp-uniform 8-bit mask from phase A; the loads are predicated, not branched,
-//     and the loads of step k+1 are issued between the interpolation and the physics of step k.
-//     Average corner loads per step at C3: 24 -> 9.8.
+//     slots of the face left behind and nothing is shuffled.  Phase A hands every step the 8 trilinear
+//     weights in slot order (24 FMAs per sample instead of 21 lerps = 42 operations) and an 8-bit mask
+//     of the slots to (re)load; the usual masks branch to unpredicated loads of exactly those slots.
+//     Average corner loads per step at C3: 24 -> 9.8 (l1tex global-load sectors 2.04e9 -> 0.86e9);
+//   * the march is software-pipelined: the loads of step k+1 are issued as soon as step k's
+//     interpolation has consumed the slots and fly during step k's physics, which shares a basic block
+//     with the interpolation of step k+1;
 //   * the ray accumulators (Faraday depth, I, Q, U) are plain registers; the Faraday depth is carried
 //     pre-multiplied by 2 lambda^2 (the rotation angle), -Pi(p) is applied once after the march, and
 //     the rotation uses short Taylor kernels whenever the whole warp's angle is below 1/8 rad;
 //   * RL = 16 / 8: the 2 / 4 lane groups march consecutive segments of the ray; when the segments are
 //     joined, each outer one is rotated by the total Faraday depth of those inside it (the rotation
 //     is linear in Q+iU).
-// Measured and dropped (first version): an L1 prefetch (CCTL.PF1) of the next step's corner lines
-// (4.24 vs 3.47 ms); 128-thread blocks at 72 registers (3.58 vs 3.47 ms); two realisation groups per
-// warp (3.88-4.24 vs 3.48 ms).
+// Measured and dropped: L1 prefetch of the lines two steps ahead, by CCTL.PF1 or by a load per line
+// (2.44 / 2.30 vs 2.31 ms: what the prefetch hides it costs in issue slots); prefetching the weights
+// into registers (spills, 5.9 ms); 12 warps / SM at 168 registers (2.70 vs 2.31 ms); first version:
+// 128-thread blocks at 72 registers, two realisation groups per warp.
 // Numeric definition: oracle/los.py.
 #include <cstdlib>
+#include <type_traits>
 #include "los.cuh"
 
-// block shape: warps (= pixels) per block and resident blocks per SM the register budget is cut for
-#ifndef IMB_LOS_WPB
-#define IMB_LOS_WPB 4
-#endif
-#ifndef IMB_LOS_MINB
-#define IMB_LOS_MINB 4
+// resident warps per SM the register budget is cut for (16: 128 registers, no spills; 20: 96
+// registers and a few spilled words outside the inner dependency chains -- faster)
+#ifndef IMB_LOS_WARPS_PER_SM
+#define IMB_LOS_WARPS_PER_SM 20
 #endif
 
 namespace imb {
 
-struct __align__(16) RlPix {   // per warp, in shared memory
+struct __align__(16) RlPix {   // per block, in shared memory
   // sky basis by its angles: n = (st cp, st sp, ct), north = (-ct cp, -ct sp, st), east = (-sp, cp, 0)
   double st, ct, cp, sp;
   double n[3];
   int j_lo, j_hi;
 };
 
-struct __align__(16) RlGeo {   // per (warp, step slot): everything realisation-independent
+struct __align__(16) RlGeo {   // per (segment, step slot): everything realisation-independent
   double w[8];                 // trilinear weight of each vertex slot
-  double ne, cre;              // 0.812 n_e dl [2 lambda^2]; CRE K(p) [dl]
+  double ne, cre;              // -0.812 n_e dl [2 lambda^2]; CRE K(p) [dl]
   int base;                    // cell index of the slot-(0,0,0) vertex (the all-even one)
   int code;                    // bits 0-7: slots to load (bit 4 sx + 2 sy + sz); 8-10: parity of ix, iy, iz;
-  int pad[2];                  // bit 11: step is inside the box
+  double dm;                   // n_e dl of the step (shared-n_e dispersion measure); bit 11 of code: inside the box
+  int pad[4];                  // 112 bytes: conflict-free 128-bit stores
 };
 
 // three predicated 64-bit loads (the x, y, z components of one vertex slot) in program order
@@ -83,17 +91,16 @@ __device__ __forceinline__ int2 lds_i2(unsigned int addr) {
   return v;
 }
 
-// kernel parameters: the LOS arguments plus the Taylor coefficients of the small-angle rotation as
-// constant-bank operands (a __constant__ array costs one LDC per coefficient and step)
+// kernel parameters: the LOS arguments plus per-launch constants as constant-bank operands
 struct RlArgs {
   LosArgs a;
-  double ts[4], tc[5];
-  int sx, sy;          // cell strides of the x and y axes (launch_los_rl guarantees ncell < 2^31)
+  double ts[4], tc[5];   // Taylor coefficients of the small-angle rotation
+  double inv_dr;
+  int sx, sy;            // cell strides of the x and y axes (launch_los_rl guarantees ncell < 2^31)
+  int n_groups;
 };
 
-// sin and cos for |x| <= 1/8: Taylor to x^9 / x^10 (truncation below 3e-17 relative).  Horner form: every
-// FMA takes its coefficient straight from the constant bank (the Estrin form needs two per FMA, i.e. an
-// LDC and a register each)
+// sin and cos for |x| <= 1/8: Taylor to x^9 / x^10 (truncation below 3e-17 relative), Horner form
 __device__ __forceinline__ void sincos_small(const RlArgs& ra, double x, double& sn, double& cs) {
   const double z = x * x;
   double ps = fma(ra.ts[3], z, ra.ts[2]), pc = fma(ra.tc[4], z, ra.tc[3]);
@@ -104,134 +111,150 @@ __device__ __forceinline__ void sincos_small(const RlArgs& ra, double x, double&
   cs = fma(z, pc, 1.0);
 }
 
+// sample j of the ray: grid coordinates and the in-box test, bit-identical to
+// oracle/los.py:sample_geometry (no fma on this path)
+struct RlCell { double px, py, pz, ux, uy, uz; int ix, iy, iz; bool inside; };
+__device__ __forceinline__ RlCell rl_cell(const LosArgs& a, const RlPix& pc, int j, bool valid) {
+  RlCell c;
+  const double r = __dmul_rn((double)j + 0.5, a.dr);
+  c.px = __dadd_rn(a.obs[0], __dmul_rn(r, pc.n[0]));
+  c.py = __dadd_rn(a.obs[1], __dmul_rn(r, pc.n[1]));
+  c.pz = __dadd_rn(a.obs[2], __dmul_rn(r, pc.n[2]));
+  c.ux = __dmul_rn(__dsub_rn(c.px, a.g.lo[0]), a.g.inv_step[0]);
+  c.uy = __dmul_rn(__dsub_rn(c.py, a.g.lo[1]), a.g.inv_step[1]);
+  c.uz = __dmul_rn(__dsub_rn(c.pz, a.g.lo[2]), a.g.inv_step[2]);
+  c.inside = valid && c.ux >= 0.0 && c.ux <= (double)(a.g.n[0] - 1) && c.uy >= 0.0 &&
+             c.uy <= (double)(a.g.n[1] - 1) && c.uz >= 0.0 && c.uz <= (double)(a.g.n[2] - 1);
+  if (!c.inside) c.ux = c.uy = c.uz = 0.0;
+  c.ix = min((int)c.ux, a.g.n[0] - 2);
+  c.iy = min((int)c.uy, a.g.n[1] - 2);
+  c.iz = min((int)c.uz, a.g.n[2] - 2);
+  return c;
+}
+
 // SHARED: every scalar grid present (n_e, CRE) is one grid for all realisations -- the usual case;
-// the per-realisation gathers of RandomThermalElectrons are then compiled out of the march
-template <int RL, bool HAS_NE, bool HAS_CRE, bool VAR_P, bool P3, bool SHARED, int WPB, int MINB>
-__global__ void __launch_bounds__(32 * WPB, MINB) los_rl_kernel(const __grid_constant__ RlArgs ra) {
+// the per-realisation gathers of RandomThermalElectrons are then compiled out of the march.
+// G: warps (realisation groups) per block.
+template <int RL, bool HAS_NE, bool HAS_CRE, bool VAR_P, bool P3, bool SHARED, int G>
+__global__ void __launch_bounds__(32 * G, IMB_LOS_WARPS_PER_SM / G)
+los_rl_kernel(const __grid_constant__ RlArgs ra) {
   const LosArgs& a = ra.a;
   constexpr int S = 32 / RL;                 // ray segments marched side by side by one warp
+  constexpr int CH = G * RL;                 // steps per segment and chunk
   constexpr unsigned int FULL = 0xffffffffu;
   constexpr unsigned int GEO = sizeof(RlGeo);
-  static_assert(sizeof(RlGeo) == 96, "RlGeo layout is addressed by byte offsets below");
-  __shared__ RlPix s_pix[WPB];
-  __shared__ RlGeo s_geo[WPB * 32 + 1];      // + 1: the march reads one step slot ahead
-  __shared__ double s_var[VAR_P ? WPB : 1][32][3];
-  __shared__ double s_dm[WPB][32];           // shared-n_e dispersion measure of each lane's steps
-  __shared__ int4 s_last[WPB][S];            // cell of the step before this chunk, per segment (w: in box)
+  static_assert(sizeof(RlGeo) == 112, "RlGeo layout is addressed by byte offsets below");
+  __shared__ RlPix s_pix;
+  __shared__ RlGeo s_geo[S * CH + 1];        // [segment][step]; + 1: the march reads one step slot ahead
+  __shared__ double s_var[VAR_P ? S * CH : 1][3];
+  __shared__ double s_dm[G][32];             // shared-n_e dispersion measure, per warp and lane (see phase B)
+  __shared__ int2 s_rng[G];                  // first / last in-box step among those each warp prepared
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int seg = lane / RL, rl = lane % RL;
-  const int pix = blockIdx.x * WPB + warp;
-  if (pix >= a.m) return;                               // whole warp exits together
-  const int g = blockIdx.y;
+  const int pix = blockIdx.x;
+  const int g = blockIdx.y * G + warp;
+  const bool active = g < ra.n_groups;       // an idle warp of the last block still helps with phase A
   const int rr = g * RL + rl;
-  const bool live = rr < a.n_real;
-  RlPix& pc = s_pix[warp];
+  const bool live = active && rr < a.n_real;
+  RlPix& pc = s_pix;
 
-  if (lane == 0) {
+  if (warp == 0) {
     const double nx = a.dirs[3 * pix], ny = a.dirs[3 * pix + 1], nz = a.dirs[3 * pix + 2];
-    const double sth = sqrt(nx * nx + ny * ny);
-    const double cph = sth > 0.0 ? nx / sth : 1.0, sph = sth > 0.0 ? ny / sth : 0.0;
-    pc.n[0] = nx; pc.n[1] = ny; pc.n[2] = nz;
-    pc.st = sth; pc.ct = nz; pc.cp = cph; pc.sp = sph;
-    // conservative in-box step range (the exact in-box test is still done per step)
+    // conservative in-box step range (the exact in-box test is still done per step): lane k < 3
+    // intersects the ray with the slab of axis k
     double tmin = 0.0, tmax = a.dr * (double)a.n_steps;
-    const double nn[3] = {nx, ny, nz};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double lo = a.g.lo[k], hi = lo + (double)(a.g.n[k] - 1) / a.g.inv_step[k];
-      if (nn[k] != 0.0) {
-        const double t1 = (lo - a.obs[k]) / nn[k], t2 = (hi - a.obs[k]) / nn[k];
+    if (lane < 3) {
+      const double nk = lane == 0 ? nx : (lane == 1 ? ny : nz);
+      const double lo = a.g.lo[lane], hi = lo + (double)(a.g.n[lane] - 1) / a.g.inv_step[lane];
+      if (nk != 0.0) {
+        const double t1 = (lo - a.obs[lane]) / nk, t2 = (hi - a.obs[lane]) / nk;
         tmin = fmax(tmin, fmin(t1, t2));
         tmax = fmin(tmax, fmax(t1, t2));
-      } else if (a.obs[k] < lo || a.obs[k] > hi) {
+      } else if (a.obs[lane] < lo || a.obs[lane] > hi) {
         tmax = -1.0;
       }
     }
-    int j_lo = 0, j_hi = -1;
-    if (tmax >= tmin) {
-      j_lo = max(0, (int)floor(tmin / a.dr - 0.5) - 1);
-      j_hi = min(a.n_steps - 1, (int)ceil(tmax / a.dr - 0.5) + 1);
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+      tmin = fmax(tmin, __shfl_xor_sync(FULL, tmin, o));
+      tmax = fmin(tmax, __shfl_xor_sync(FULL, tmax, o));
     }
-    pc.j_lo = j_lo; pc.j_hi = j_hi;
+    if (lane == 0) {
+      const double sth = sqrt(nx * nx + ny * ny);
+      pc.n[0] = nx; pc.n[1] = ny; pc.n[2] = nz;
+      pc.st = sth; pc.ct = nz;
+      pc.cp = sth > 0.0 ? nx / sth : 1.0;
+      pc.sp = sth > 0.0 ? ny / sth : 0.0;
+      int j_lo = 0, j_hi = -1;
+      if (tmax >= tmin) {
+        j_lo = max(0, (int)floor(tmin * ra.inv_dr - 0.5) - 1);
+        j_hi = min(a.n_steps - 1, (int)ceil(tmax * ra.inv_dr - 0.5) + 1);
+      }
+      pc.j_lo = j_lo; pc.j_hi = j_hi;
+    }
   }
-  __syncwarp();
+  s_dm[warp][lane] = 0.0;
+  __syncthreads();
 
   const int seg_len = (pc.j_hi - pc.j_lo + 1 + S - 1) / S;     // <= 0 when the ray misses the box
   const int sy = ra.sy, sx = ra.sx;
   const bool ne_shared = HAS_NE && (SHARED || a.ne_row == 0), cre_shared = HAS_CRE && (SHARED || a.cre_row == 0);
   constexpr long long CS = 3 * RL;                       // doubles per vertex of the wide layout
-  const double* __restrict__ Bg = a.B + (long long)g * a.g.ncell * CS + rl;
-  // shared-memory byte address of this lane group's first step slot
-  unsigned int geo_seg = (unsigned int)__cvta_generic_to_shared(&s_geo[warp * 32 + seg * RL]);
+  const double* __restrict__ Bg = a.B + (long long)(active ? g : 0) * a.g.ncell * CS + rl;
+  // shared-memory byte address of this lane group's (segment's) first step slot
+  const unsigned int geo_seg = (unsigned int)__cvta_generic_to_shared(&s_geo[seg * CH]);
 
-  // the Faraday depth is carried as the rotation angle 2 lambda^2 phi when it rotates anything
   const double st = pc.st, ct = pc.ct, cp = pc.cp, sp = pc.sp;
-  s_dm[warp][lane] = 0.0;
-  if (rl == RL - 1) s_last[warp][seg] = make_int4(0, 0, 0, 0);
-  __syncwarp();
+  // the Faraday depth is carried as the rotation angle 2 lambda^2 phi when it rotates anything
   double carry = 0.0, dm = 0.0, I = 0.0, Q = 0.0, U = 0.0;
   // the resident cell: v[slot][component], slot = 4 (X&1) + 2 (Y&1) + (Z&1)
   double v[8][3];
 #pragma unroll
   for (int s = 0; s < 8; ++s) v[s][0] = v[s][1] = v[s][2] = 0.0;
 
-  for (int cb = 0; cb < seg_len; cb += RL) {
-    // ---- phase A: lane (seg, rl) prepares step j of its segment --------------------------------
+  for (int cb = 0; cb < seg_len; cb += CH) {
+    // ---- phase A: lane (warp, seg, rl) prepares step cb + warp RL + rl of its segment ------------
     {
-      const int off = cb + rl;
+      const int istep = warp * RL + rl;                    // step slot within the chunk
+      const int off = cb + istep;
       const int j_hi = pc.j_hi;
       const int j = pc.j_lo + seg * seg_len + off;
-      // geometry: bit-identical to oracle/los.py:sample_geometry (no fma on this path)
-      const double r = __dmul_rn((double)j + 0.5, a.dr);
-      const double px = __dadd_rn(a.obs[0], __dmul_rn(r, pc.n[0]));
-      const double py = __dadd_rn(a.obs[1], __dmul_rn(r, pc.n[1]));
-      const double pz = __dadd_rn(a.obs[2], __dmul_rn(r, pc.n[2]));
-      double ux = __dmul_rn(__dsub_rn(px, a.g.lo[0]), a.g.inv_step[0]);
-      double uy = __dmul_rn(__dsub_rn(py, a.g.lo[1]), a.g.inv_step[1]);
-      double uz = __dmul_rn(__dsub_rn(pz, a.g.lo[2]), a.g.inv_step[2]);
-      const bool inside = off < seg_len && j <= j_hi && ux >= 0.0 && ux <= (double)(a.g.n[0] - 1) &&
-                          uy >= 0.0 && uy <= (double)(a.g.n[1] - 1) && uz >= 0.0 &&
-                          uz <= (double)(a.g.n[2] - 1);
-      if (!inside) ux = uy = uz = 0.0;
-      const int ix = min((int)ux, a.g.n[0] - 2), iy = min((int)uy, a.g.n[1] - 2),
-                iz = min((int)uz, a.g.n[2] - 2);
-      Cell c;
-      c.base = ((long long)ix * a.g.n[1] + iy) * a.g.n[2] + iz;
-      c.sy = sy; c.sx = sx;
-      c.tx = ux - (double)ix; c.ty = uy - (double)iy; c.tz = uz - (double)iz;
+      const RlCell c = rl_cell(a, pc, j, off < seg_len && j <= j_hi);
+      const int ix = c.ix, iy = c.iy, iz = c.iz;
+      const bool inside = c.inside;
+      Cell cc;
+      cc.base = ((long long)ix * a.g.n[1] + iy) * a.g.n[2] + iz;
+      cc.sy = sy; cc.sx = sx;
+      cc.tx = c.ux - (double)ix; cc.ty = c.uy - (double)iy; cc.tz = c.uz - (double)iz;
       double ne_s = 0.0, cre_s = 0.0;
       if (inside) {
         if (HAS_NE && HAS_CRE && a.necre) {
-          interp_pair(a.necre, c, ne_s, cre_s);
+          interp_pair(a.necre, cc, ne_s, cre_s);
         } else {
-          if (ne_shared) ne_s = interp_scalar(a.ne, c);
-          if (cre_shared) cre_s = interp_scalar(a.cre, c);
+          if (ne_shared) ne_s = interp_scalar(a.ne, cc);
+          if (cre_shared) cre_s = interp_scalar(a.cre, cc);
         }
       }
-      if (ne_shared) s_dm[warp][lane] += ne_s * a.dl_pc;
       double kp = a.sync_k;
       if (HAS_CRE && VAR_P) {
-        const double R = sqrt(px * px + py * py);
-        const double p = a.alpha - a.beta * R - a.theta * pz;
+        const double R = sqrt(c.px * c.px + c.py * c.py);
+        const double p = a.alpha - a.beta * R - a.theta * c.pz;
         kp = inside ? sync_coeff_var(a, p) : 0.0;
-        s_var[warp][lane][0] = kp;
-        s_var[warp][lane][1] = (p + 1.0) / (p + 7.0 / 3.0);
-        s_var[warp][lane][2] = (p + 1.0) * 0.25;
+        s_var[seg * CH + istep][0] = kp;
+        s_var[seg * CH + istep][1] = (p + 1.0) / (p + 7.0 / 3.0);
+        s_var[seg * CH + istep][2] = (p + 1.0) * 0.25;
       }
-      // which slots hold a different vertex than after the previous step of this segment
-      int pix_ = __shfl_up_sync(FULL, ix, 1), piy_ = __shfl_up_sync(FULL, iy, 1),
-          piz_ = __shfl_up_sync(FULL, iz, 1), pin_ = __shfl_up_sync(FULL, (int)inside, 1);
-      if (rl == 0) { const int4 l = s_last[warp][seg]; pix_ = l.x; piy_ = l.y; piz_ = l.z; pin_ = l.w; }
-      __syncwarp();
-      if (rl == RL - 1) s_last[warp][seg] = make_int4(ix, iy, iz, (int)inside);
+      // which slots hold a different vertex than after the previous step of this segment (its cell is
+      // recomputed here: cheaper than passing it between lanes and warps)
       const int qx = ix & 1, qy = iy & 1, qz = iz & 1;
       int code = 0;
       if (inside) {
         int cx = 3, cy = 3, cz = 3;                        // bit s: the vertex of parity s changed
-        if (pin_) {
-          cx = (ix + qx != pix_ + (pix_ & 1) ? 1 : 0) | (ix + 1 - qx != pix_ + 1 - (pix_ & 1) ? 2 : 0);
-          cy = (iy + qy != piy_ + (piy_ & 1) ? 1 : 0) | (iy + 1 - qy != piy_ + 1 - (piy_ & 1) ? 2 : 0);
-          cz = (iz + qz != piz_ + (piz_ & 1) ? 1 : 0) | (iz + 1 - qz != piz_ + 1 - (piz_ & 1) ? 2 : 0);
+        const RlCell pr = rl_cell(a, pc, j - 1, off > 0);
+        if (pr.inside) {
+          cx = (ix + qx != pr.ix + (pr.ix & 1) ? 1 : 0) | (ix + 1 - qx != pr.ix + 1 - (pr.ix & 1) ? 2 : 0);
+          cy = (iy + qy != pr.iy + (pr.iy & 1) ? 1 : 0) | (iy + 1 - qy != pr.iy + 1 - (pr.iy & 1) ? 2 : 0);
+          cz = (iz + qz != pr.iz + (pr.iz & 1) ? 1 : 0) | (iz + 1 - qz != pr.iz + 1 - (pr.iz & 1) ? 2 : 0);
         }
 #pragma unroll
         for (int s = 0; s < 8; ++s)
@@ -239,10 +262,10 @@ __global__ void __launch_bounds__(32 * WPB, MINB) los_rl_kernel(const __grid_con
         code |= (qx << 8) | (qy << 9) | (qz << 10) | (1 << 11);
       }
       // the slot of parity s along an axis holds the vertex i (weight 1 - t) when s == i & 1, else i + 1 (t)
-      RlGeo& ge = s_geo[warp * 32 + lane];
-      const double wx[2] = {qx ? c.tx : 1.0 - c.tx, qx ? 1.0 - c.tx : c.tx};
-      const double wy[2] = {qy ? c.ty : 1.0 - c.ty, qy ? 1.0 - c.ty : c.ty};
-      const double wz[2] = {qz ? c.tz : 1.0 - c.tz, qz ? 1.0 - c.tz : c.tz};
+      RlGeo& ge = s_geo[seg * CH + istep];
+      const double wx[2] = {qx ? cc.tx : 1.0 - cc.tx, qx ? 1.0 - cc.tx : cc.tx};
+      const double wy[2] = {qy ? cc.ty : 1.0 - cc.ty, qy ? 1.0 - cc.ty : cc.ty};
+      const double wz[2] = {qz ? cc.tz : 1.0 - cc.tz, qz ? 1.0 - cc.tz : cc.tz};
 #pragma unroll
       for (int s = 0; s < 8; ++s) ge.w[s] = wx[s >> 2] * wy[(s >> 1) & 1] * wz[s & 1];
       const double dlf = a.dl_pc * ((HAS_NE && HAS_CRE) ? 2.0 * a.lam2 : 1.0);
@@ -250,45 +273,79 @@ __global__ void __launch_bounds__(32 * WPB, MINB) los_rl_kernel(const __grid_con
       // -0.812 n_e dl [2 lambda^2] (Faraday; the sign of B_par = -B.n rides along) and CRE K(p) [dl]
       ge.ne = -(__dmul_rn(0.812, ne_s) * dlf);
       ge.cre = P3 ? cre_s * kp * a.dl_cm : cre_s * kp;
-      ge.base = (int)c.base + qx * sx + qy * sy + qz;
+      ge.base = (int)cc.base + qx * sx + qy * sy + qz;
       ge.code = code;
+      ge.dm = ne_s * a.dl_pc;
+      // in-box steps among those this warp prepared, any segment
+      const unsigned int mask = __ballot_sync(FULL, inside);
+      unsigned int u = 0;
+#pragma unroll
+      for (int q = 0; q < S; ++q) u |= (mask >> (q * RL)) & ((RL < 32 ? (1u << RL) : 0u) - 1u);
+      if (lane == 0) s_rng[warp] = u ? make_int2(warp * RL + __ffs(u) - 1, warp * RL + 31 - __clz(u))
+                                     : make_int2(CH, -1);
     }
-    __syncwarp();
+    __syncthreads();
 
     // ---- phase B: march the in-box steps of this chunk, one realisation per lane ----------------
     // Software pipeline: the physics of step k-1 and the interpolation of step k are independent, so
-    // they sit in ONE basic block and the scheduler interleaves them (DFMA latency 8.3 clk, 4 warps
-    // per scheduler: a single dependent chain per warp leaves the FP64 pipe half idle); the loads of
-    // step k+1 are issued as soon as step k's interpolation has consumed the slots.
-    unsigned int todo = 0;
-    {
-      const unsigned int mask = __ballot_sync(FULL, (s_geo[warp * 32 + lane].code >> 11) & 1);
-      if (S == 1) {
-        todo = mask;
-      } else {
+    // they sit in ONE basic block; the loads of step k+1 are issued as soon as step k's
+    // interpolation has consumed the slots.
+    int first = CH, last = -1;
 #pragma unroll
-        for (int q = 0; q < S; ++q) todo |= (mask >> (q * RL)) & ((RL < 32 ? (1u << RL) : 0u) - 1u);
-      }
+    for (int w = 0; w < G; ++w) { const int2 r = s_rng[w]; first = min(first, r.x); last = max(last, r.y); }
+    if (ne_shared) {
+      // dispersion measure: lane l sums the steps = l (mod RL) of its segment in step order, whatever G
+      // is (the maps of a realisation must not depend on how the ensemble is sharded, bit for bit)
+      double acc = s_dm[warp][lane];
+#pragma unroll
+      for (int w = 0; w < G; ++w) acc += s_geo[seg * CH + w * RL + rl].dm;
+      s_dm[warp][lane] = acc;
     }
-    if (todo) {
+#ifdef IMB_LOS_DBG_ONLYA
+    last = -1;
+#endif
+    if (active && last >= first) {
       // the in-box steps of a ray are contiguous (the box is convex): march first .. last; a step in
       // between that no segment has in the box carries zero factors and an empty load mask
-      const int first = __ffs(todo) - 1;
-      int n_left = (31 - __clz(todo)) - first;               // steps after the current one
-      int sl = seg * RL + first;                              // step slot within the warp (VAR_P)
+      int n_left = last - first;                              // steps after the current one
+      int sl = seg * CH + first;                              // step slot (VAR_P)
       unsigned int ga = geo_seg + (unsigned int)first * GEO;  // shared address of the current RlGeo
-      // (re)load the slots whose vertex changed; S == 1: the mask is warp-uniform, skip all when empty
-      auto fetch = [&](const int2 bc) {
-        const int base = bc.x, code = bc.y;
-        if (S == 1 && (code & 0xff) == 0) return;
-#ifdef IMB_LOS_DBG_NOLOAD
-        if (base >= 0) return;
-#endif
+      // (re)load the slots whose vertex changed.  S == 1: the mask is warp-uniform; the usual masks (one
+      // face crossed, everything) branch to unpredicated loads of exactly those slots -- a predicated-off
+      // LDG still takes an issue slot and a pass through the LSU data pipe (ncu: 65 M of them per launch)
+      auto fetch_mask = [&](const int base, const int code, auto mask_c) {
+        constexpr int M = decltype(mask_c)::value;
         const int dx = (code & 0x100) ? -sx : sx, dy = (code & 0x200) ? -sy : sy, dz = (code & 0x400) ? -1 : 1;
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
+          if (!(M & (1 << s))) continue;
           const int idx = base + ((s & 4) ? dx : 0) + ((s & 2) ? dy : 0) + ((s & 1) ? dz : 0);
-          load_slot<RL>(v[s][0], v[s][1], v[s][2], Bg + (long long)idx * CS, code & (1 << s));
+          const double* p = Bg + (long long)idx * CS;
+          if (M == 0x1ff) {                        // generic: predicated per slot
+            load_slot<RL>(v[s][0], v[s][1], v[s][2], p, code & (1 << s));
+          } else {
+            v[s][0] = ldg64(p); v[s][1] = ldg64(p + RL); v[s][2] = ldg64(p + 2 * RL);
+          }
+        }
+      };
+      auto fetch = [&](const int2 bc) {
+        const int base = bc.x, code = bc.y;
+#ifdef IMB_LOS_DBG_NOLOAD
+        if (base >= 0) return;
+#endif
+        if (S == 1) {
+          const int m = code & 0xff;
+          if (m == 0) return;
+          if (m == 0x55) fetch_mask(base, code, std::integral_constant<int, 0x55>());        // z face
+          else if (m == 0xaa) fetch_mask(base, code, std::integral_constant<int, 0xaa>());
+          else if (m == 0x33) fetch_mask(base, code, std::integral_constant<int, 0x33>());   // y face
+          else if (m == 0xcc) fetch_mask(base, code, std::integral_constant<int, 0xcc>());
+          else if (m == 0x0f) fetch_mask(base, code, std::integral_constant<int, 0x0f>());   // x face
+          else if (m == 0xf0) fetch_mask(base, code, std::integral_constant<int, 0xf0>());
+          else if (m == 0xff) fetch_mask(base, code, std::integral_constant<int, 0xff>());
+          else fetch_mask(base, code, std::integral_constant<int, 0x1ff>());
+        } else {
+          fetch_mask(base, code, std::integral_constant<int, 0x1ff>());
         }
       };
       // per-realisation scalar grids (RandomThermalElectrons): same slots, same weights
@@ -353,7 +410,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) los_rl_kernel(const __grid_con
         if (HAS_CRE) {
           double ck = p.ck;                                  // CRE K(p) dl (P3) or CRE K(p)
           if (!cre_shared) {
-            const double kp = VAR_P ? s_var[warp][p.sl][0] : a.sync_k;
+            const double kp = VAR_P ? s_var[p.sl][0] : a.sync_k;
             ck = P3 ? p.cre_r * kp * a.dl_cm : p.cre_r * kp;
           }
           const double bn = fma(st, p.bz, -(ct * bh));       // B . north
@@ -367,11 +424,11 @@ __global__ void __launch_bounds__(32 * WPB, MINB) los_rl_kernel(const __grid_con
             I = fma(ck, bp2, I);
             gq = ck;
           } else {
-            const double expo = VAR_P ? s_var[warp][p.sl][2] : a.expo;
+            const double expo = VAR_P ? s_var[p.sl][2] : a.expo;
             const double em = bp2 > 0.0 ? ck * pow(bp2, expo) * a.dl_cm : 0.0;
             I += em;
             gq = bp2 > 0.0 ? em / bp2 : 0.0;
-            if (VAR_P) gq *= s_var[warp][p.sl][1];
+            if (VAR_P) gq *= s_var[p.sl][1];
           }
           const double qc = gq * dq, uc = gq * du;
           if (HAS_NE) {
@@ -402,7 +459,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) los_rl_kernel(const __grid_con
       }
       physics(prev);
     }
-    __syncwarp();                                        // phase A of the next chunk reuses s_geo
+    __syncthreads();                                     // phase A of the next chunk reuses s_geo
   }
 
   if (HAS_CRE) {
@@ -430,10 +487,10 @@ __global__ void __launch_bounds__(32 * WPB, MINB) los_rl_kernel(const __grid_con
     }
   }
   if (ne_shared) {
-    double dm_geo = s_dm[warp][lane];
+    double part = s_dm[warp][lane];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) dm_geo += __shfl_xor_sync(FULL, dm_geo, o);
-    dm = dm_geo;
+    for (int o = 1; o < 32; o <<= 1) part += __shfl_xor_sync(FULL, part, o);
+    dm = part;
   }
   if (seg == 0 && live) {
     const long long o = out_index(a, rr, pix);
@@ -451,9 +508,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) los_rl_kernel(const __grid_con
 
 template <int RL, bool HAS_NE, bool HAS_CRE, bool VAR_P, bool P3>
 static int launch_rl_variant(const LosArgs& a, cudaStream_t s) {
-  constexpr int WPB = IMB_LOS_WPB, MINB = IMB_LOS_MINB;
   const int n_groups = (a.n_real + RL - 1) / RL;
-  dim3 grid((a.m + WPB - 1) / WPB, n_groups);
   RlArgs ra;
   ra.a = a;
   // Taylor coefficients of sin (x^3 .. x^9) and cos (x^2 .. x^10)
@@ -461,11 +516,20 @@ static int launch_rl_variant(const LosArgs& a, cudaStream_t s) {
   const double tc[5] = {-0.5, 1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0};
   for (int k = 0; k < 4; ++k) ra.ts[k] = ts[k];
   for (int k = 0; k < 5; ++k) ra.tc[k] = tc[k];
+  ra.inv_dr = 1.0 / a.dr;
   ra.sy = a.g.n[2];
   ra.sx = a.g.n[1] * a.g.n[2];
+  ra.n_groups = n_groups;
   const bool shared = (!HAS_NE || a.ne_row == 0) && (!HAS_CRE || a.cre_row == 0);
-  if (shared) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, WPB, MINB><<<grid, 32 * WPB, 0, s>>>(ra);
-  else los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, false, WPB, MINB><<<grid, 32 * WPB, 0, s>>>(ra);
+  if (RL == 32 && shared && n_groups >= 2) {
+    // two realisation groups of a pixel share one geometry pass
+    dim3 grid(a.m, (n_groups + 1) / 2);
+    los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, (RL == 32 ? 2 : 1)><<<grid, 64, 0, s>>>(ra);
+    return IMB_OK;
+  }
+  dim3 grid(a.m, n_groups);
+  if (shared) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, 1><<<grid, 32, 0, s>>>(ra);
+  else los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, false, 1><<<grid, 32, 0, s>>>(ra);
   return IMB_OK;
 }
 
@@ -486,6 +550,7 @@ static int launch_rl(const LosArgs& a, bool has_ne, bool has_cre, bool var_p, cu
 // entry used by imb_los_integrate for b_stride == 96 (RL 32), 48 (RL 16) and 24 (RL 8)
 int launch_los_rl(const LosArgs& a, int rl, bool has_ne, bool has_cre, bool var_p, cudaStream_t s) {
   if (a.g.ncell >= (1ll << 31)) return IMB_EUNSUPPORTED;      // 32-bit cell index in RlGeo
+  if ((a.n_real + rl - 1) / rl > 65535) return IMB_EUNSUPPORTED;   // grid.y
   if (rl == 32) return launch_rl<32>(a, has_ne, has_cre, var_p, s);
   if (rl == 16) return launch_rl<16>(a, has_ne, has_cre, var_p, s);
   return launch_rl<8>(a, has_ne, has_cre, var_p, s);

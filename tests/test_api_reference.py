@@ -8,13 +8,13 @@ import pickle
 import numpy as np
 import pytest
 
-from imagine_b200.api import mirror as M
+import imagine_b200.api as M
 from imagine_b200.api import units as u
 
 
 def test_basedict_is_abstract():
     with pytest.raises(TypeError):
-        M.ObservableDict()
+        __import__("imagine.observables").observables.ObservableDict()
 
 
 def test_observable_semantics():
