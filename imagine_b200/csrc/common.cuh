@@ -138,75 +138,72 @@ __device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {
 
 // ---- Box-Muller pair of block `blk` of stream `stream` under `seed` ------------------------
 // z0 + i z1 = sqrt(-2 ln u1) exp(2 pi i u2) with u = (k + 1/2) 2^-52 from 52 random bits each
-// (oracle/fields.py:philox_normal_blocks).  log and sin/cos are evaluated directly on the
-// integer random bits: exponent by count-leading-zeros, exact quadrant reduction, short Taylor
-// kernels with constant-bank coefficients.  |error| <= 2 ulp; ~2x fewer instructions than
-// log() + sincospi() of the CUDA math library, which this kernel is bound by.
+// (oracle/fields.py:philox_normal_blocks).  log and sin/cos are evaluated directly on the integer
+// random bits with TABLE-DRIVEN range reduction (a 129-entry table of (1/c, ln c), c = 1 + i/128,
+// and a 257-entry table of (cos, sin)(pi j/128), 6 KB, staged in shared memory by every block):
+//   ln u   = e ln 2 + ln c_i + log1p(m/c_i - 1),  |m/c_i - 1| <= 2^-8   -> degree-7 series
+//   angle  = pi j/128 + x, |x| <= pi/256                                  -> sin to x^5, cos to x^6,
+//            then one rotation by the tabulated (cos, sin)
+// |error| <= 4e-16 absolute on ln u (relative 2^-52 next to u = 1, where c = 2 and e = -1 cancel
+// exactly), <= 3e-16 on sin/cos.  The field kernel is instruction-issue bound: this is ~45 instead
+// of ~95 instructions for the two transcendentals of a pair (the first version used a division and
+// degree-9 / degree-13 polynomials; the CUDA library's log + sincospi take ~2x that again).
 __device__ __constant__ double kSinC[7] = {-0.16666666666666666, 0.008333333333333333,
     -0.0001984126984126984, 2.7557319223985893e-06, -2.505210838544172e-08,
     1.6059043836821613e-10, -7.647163731819816e-13};
 __device__ __constant__ double kCosC[8] = {-0.5, 0.041666666666666664, -0.001388888888888889,
     2.48015873015873e-05, -2.755731922398589e-07, 2.08767569878681e-09,
     -1.1470745597729725e-11, 4.779477332387385e-14};
-__device__ __constant__ double kLogC[10] = {1.0, 0.3333333333333333, 0.2, 0.14285714285714285,
-    0.1111111111111111, 0.09090909090909091, 0.07692307692307693, 0.06666666666666667,
-    0.058823529411764705, 0.05263157894736842};
 
-// n / d for d in [1.7, 2.5] (no special cases to guard): hardware reciprocal seed (2^-23), two
-// Newton steps, one residual correction; within 1 ulp of the IEEE quotient in ~half the instructions
-__device__ __forceinline__ double div_near2(double n, double d) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  double e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  const double q = n * y;
-  return fma(fma(-d, q, n), y, q);
-}
+constexpr int kTabLog = 0;       // 129 entries (1/c_i, ln c_i)
+constexpr int kTabTrig = 129;    // 257 entries (cos, sin)(pi j / 128)
+constexpr int kTabSize = 386;
+constexpr double kLn2 = 0.6931471805599453;
 
 // ln(K * 2^-53) for an odd 53-bit integer K (so the argument is in (0, 1))
-__device__ __forceinline__ double log_u53(unsigned long long K) {
+__device__ __forceinline__ double log_u53(unsigned long long K, const double2* __restrict__ tab) {
   const int p = 63 - __clzll((long long)K);                    // top bit, 0..52
-  unsigned long long bits = ((K << (52 - p)) & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull;
-  int e = p - 53;
-  double m = __longlong_as_double((long long)bits);            // [1, 2)
-  if (m > 1.4142135623730951) { m *= 0.5; e += 1; }            // [sqrt(1/2), sqrt(2)]
-  const double s = div_near2(m - 1.0, m + 1.0), z = s * s;
-  double q = kLogC[9];
-#pragma unroll
-  for (int k = 8; k >= 0; --k) q = fma(q, z, kLogC[k]);
-  return fma((double)e, 0.6931471805599453, 2.0 * s * q);
+  const unsigned long long frac = (K << (52 - p)) & 0x000FFFFFFFFFFFFFull;
+  const int i = ((int)(frac >> 44) + 1) >> 1;                  // round((m - 1) 128), 0..128
+  const double m = __longlong_as_double((long long)(frac | 0x3FF0000000000000ull));   // [1, 2)
+  const double2 t = tab[kTabLog + i];
+  const double r = fma(m, t.x, -1.0);                          // m / c_i - 1 (c_i := 1 / t.x exactly)
+  double q = 0.14285714285714285;
+  q = fma(q, r, -0.16666666666666666);
+  q = fma(q, r, 0.2);
+  q = fma(q, r, -0.25);
+  q = fma(q, r, 0.3333333333333333);
+  q = fma(q, r, -0.5);
+  const double lp = fma(r * r, q, r);                          // log1p(r)
+  return fma((double)(p - 53), kLn2, t.y) + lp;                // (e, i) = (-1, 128): exactly 0 + lp
 }
 
 // (cos, sin)(pi * K * 2^-52) for an odd 53-bit integer K (angle in (0, 2 pi))
-__device__ __forceinline__ void sincos_u53(unsigned long long K, double& sn, double& cs) {
-  int q = (int)(K >> 51);                                      // quadrant: floor(2 t)
-  const unsigned long long fr = K & 0x0007FFFFFFFFFFFFull;     // t - q/2 = fr * 2^-52 in [0, 1/2)
-  double f = (double)(long long)fr * 2.220446049250313e-16;
-  if (f > 0.25) { f -= 0.5; q += 1; }                          // |f| <= 1/4, exact
-  const double x = f * 3.141592653589793, z = x * x;
-  double ps = kSinC[6], pc = kCosC[7];
-#pragma unroll
-  for (int k = 5; k >= 0; --k) ps = fma(ps, z, kSinC[k]);
-#pragma unroll
-  for (int k = 6; k >= 0; --k) pc = fma(pc, z, kCosC[k]);
-  const double s0 = fma(x * z, ps, x), c0 = fma(z, pc, 1.0);
-  // rotate by q * pi/2
-  const double s1 = (q & 1) ? c0 : s0, c1 = (q & 1) ? s0 : c0;
-  sn = (q & 2) ? -s1 : s1;
-  cs = ((q + 1) & 2) ? -c1 : c1;
+__device__ __forceinline__ void sincos_u53(unsigned long long K, const double2* __restrict__ tab,
+                                           double& sn, double& cs) {
+  const int j = (int)((K + (1ull << 44)) >> 45);               // round(t 128), t = K 2^-52 in (0, 2)
+  const long long d = (long long)K - ((long long)j << 45);     // |d| <= 2^44, exact
+  // (double)d by the 2^52 + 2^51 offset trick (two integer adds and one DADD)
+  const double df = __longlong_as_double(0x4338000000000000ll + d) - 6755399441055744.0;
+  const double x = df * 6.975736996017264e-16;                 // pi 2^-52
+  const double2 cj = tab[kTabTrig + j];
+  const double z = x * x;
+  const double sl = fma(x * z, fma(z, 0.008333333333333333, -0.16666666666666666), x);
+  const double cl = fma(z, fma(z, fma(z, -0.001388888888888889, 0.041666666666666664), -0.5), 1.0);
+  cs = fma(cj.x, cl, -(cj.y * sl));
+  sn = fma(cj.y, cl, cj.x * sl);
 }
 
 __device__ __forceinline__ void philox_normal_pair(unsigned long long seed, uint32_t stream,
-                                                   unsigned long long blk, double& z0, double& z1) {
+                                                   unsigned long long blk, const double2* __restrict__ tab,
+                                                   double& z0, double& z1) {
   const uint4 x = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), stream, 0u),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const unsigned long long k1 = ((unsigned long long)x.x << 20) | (unsigned long long)(x.y >> 12);
   const unsigned long long k2 = ((unsigned long long)x.z << 20) | (unsigned long long)(x.w >> 12);
-  const double r = sqrt(-2.0 * log_u53(2 * k1 + 1));           // u1 = (2 k1 + 1) 2^-53
+  const double r = sqrt(-2.0 * log_u53(2 * k1 + 1, tab));      // u1 = (2 k1 + 1) 2^-53
   double s, c;
-  sincos_u53(2 * k2 + 1, s, c);                                // 2 u2 = (2 k2 + 1) 2^-52
+  sincos_u53(2 * k2 + 1, tab, s, c);                           // 2 u2 = (2 k2 + 1) 2^-52
   z0 = r * c;
   z1 = r * s;
 }

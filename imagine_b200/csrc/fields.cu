@@ -9,6 +9,15 @@
 
 namespace imb {
 
+// range-reduction tables of the Box-Muller transform (common.cuh), filled once by the host
+__device__ double2 g_normal_tab[kTabSize];
+
+// every block stages the tables in shared memory (random 16-byte reads: conflicts, not cache misses)
+__device__ __forceinline__ void stage_normal_tab(double2* s_tab) {
+  for (int k = threadIdx.x; k < kTabSize; k += blockDim.x) s_tab[k] = g_normal_tab[k];
+  __syncthreads();
+}
+
 struct FieldArgs {
   DevGrid g;
   int nfields;
@@ -28,13 +37,13 @@ struct FieldArgs {
 
 // the six normals of cell pair q of one realisation: v = [csum +] (z sigma + mu)
 __device__ __forceinline__ void simple_pair(const FieldArgs& a, unsigned long long seed, unsigned int q,
-                                            double* v) {
+                                            const double2* tab, double* v) {
   const double mu = a.p[a.gauss][0], sigma = a.p[a.gauss][1];
   const unsigned int stream = a.stream[a.gauss];
 #pragma unroll
   for (int b = 0; b < 3; ++b) {
     double z0, z1;
-    philox_normal_pair(seed, stream, 3ull * q + b, z0, z1);
+    philox_normal_pair(seed, stream, 3ull * q + b, tab, z0, z1);
     v[2 * b] = __dadd_rn(__dmul_rn(z0, sigma), mu);
     v[2 * b + 1] = __dadd_rn(__dmul_rn(z1, sigma), mu);
   }
@@ -91,6 +100,8 @@ __device__ __forceinline__ void lsa_pair(const DevGrid& g, const double* p, long
 template <int BS, bool VEC>
 __global__ void __launch_bounds__(256) field_b_kernel(const __grid_constant__ FieldArgs a,
                                                        double* __restrict__ out) {
+  __shared__ double2 s_tab[kTabSize];
+  stage_normal_tab(s_tab);
   const long long npair = (a.g.ncell + 1) >> 1;
   const long long total = npair * a.rows;
   for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
@@ -112,7 +123,7 @@ __global__ void __launch_bounds__(256) field_b_kernel(const __grid_constant__ Fi
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
           double z0, z1;
-          philox_normal_pair(seed, a.stream[f], (unsigned long long)(3 * q + b), z0, z1);
+          philox_normal_pair(seed, a.stream[f], (unsigned long long)(3 * q + b), s_tab, z0, z1);
           t[2 * b] = __dadd_rn(__dmul_rn(z0, sigma), mu);
           t[2 * b + 1] = __dadd_rn(__dmul_rn(z1, sigma), mu);
         }
@@ -147,7 +158,8 @@ __global__ void __launch_bounds__(256) field_b_kernel(const __grid_constant__ Fi
 }
 
 // the same-type sum of all magnetic fields for cell pair q of realisation r (any field list)
-__device__ __forceinline__ void generic_pair(const FieldArgs& a, unsigned int q, int r, double* v) {
+__device__ __forceinline__ void generic_pair(const FieldArgs& a, unsigned int q, int r, const double2* tab,
+                                             double* v) {
   bool first = true;
   for (int f = 0; f < a.nfields; ++f) {
     double t[6];
@@ -162,7 +174,7 @@ __device__ __forceinline__ void generic_pair(const FieldArgs& a, unsigned int q,
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
         double z0, z1;
-        philox_normal_pair(seed, a.stream[f], 3ull * q + b, z0, z1);
+        philox_normal_pair(seed, a.stream[f], 3ull * q + b, tab, z0, z1);
         t[2 * b] = __dadd_rn(__dmul_rn(z0, sigma), mu);
         t[2 * b + 1] = __dadd_rn(__dmul_rn(z1, sigma), mu);
       }
@@ -185,6 +197,8 @@ __device__ __forceinline__ void generic_pair(const FieldArgs& a, unsigned int q,
 template <int RL>
 __global__ void __launch_bounds__(256) field_b_il_kernel(const __grid_constant__ FieldArgs a,
                                                          double* __restrict__ out) {
+  __shared__ double2 s_tab[kTabSize];
+  stage_normal_tab(s_tab);
   const unsigned int npair_rl = (unsigned int)((a.g.ncell + 1) >> 1) * (unsigned int)RL;
   const int g = blockIdx.y;
   const int rl = (int)(threadIdx.x % RL), r = g * RL + rl;
@@ -196,8 +210,8 @@ __global__ void __launch_bounds__(256) field_b_il_kernel(const __grid_constant__
     const unsigned int q = w / RL;
     double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (live) {
-      if (simple) simple_pair(a, seed, q, v);
-      else generic_pair(a, q, r, v);
+      if (simple) simple_pair(a, seed, q, s_tab, v);
+      else generic_pair(a, q, r, s_tab, v);
     }
     const long long c0 = 2ll * q;
     const bool has2 = c0 + 1 < a.g.ncell;
@@ -244,6 +258,8 @@ __device__ __forceinline__ double scalar_model(const FieldArgs& a, int f, double
 template <bool VEC>
 __global__ void __launch_bounds__(256) field_scalar_kernel(const __grid_constant__ FieldArgs a,
                                                             double* __restrict__ out) {
+  __shared__ double2 s_tab[kTabSize];
+  stage_normal_tab(s_tab);
   const long long npair = (a.g.ncell + 1) >> 1;
   const long long total = npair * a.rows;
   for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
@@ -262,7 +278,7 @@ __global__ void __launch_bounds__(256) field_scalar_kernel(const __grid_constant
       if (a.kind[f] == IMB_FIELD_RANDOM_NE) {
         double n0, n1;
         philox_normal_pair(a.seeds[(size_t)a.seed_row[f] * a.n_real + r], a.stream[f],
-                           (unsigned long long)q, n0, n1);
+                           (unsigned long long)q, s_tab, n0, n1);
         t0 = __dadd_rn(__dmul_rn(n0, a.p[f][1]), a.p[f][0]);
         t1 = __dadd_rn(__dmul_rn(n1, a.p[f][1]), a.p[f][0]);
         const double mn = a.p[f][2];
@@ -415,6 +431,33 @@ static bool is_stochastic(int kind) {
   return kind == IMB_FIELD_GAUSS_B || kind == IMB_FIELD_RANDOM_NE;
 }
 
+// (1/c_i, ln c_i) with c_i := 1 / fl(1 / (1 + i/128)) and (cos, sin)(pi j / 128), rounded from long double
+static int upload_normal_tab() {
+  static bool ready = false;
+  if (ready) return IMB_OK;
+  static double2 h[kTabSize];
+  for (int i = 0; i <= 128; ++i) {
+    const double inv_c = (double)(1.0L / (1.0L + (long double)i / 128.0L));
+    h[kTabLog + i].x = inv_c;
+    h[kTabLog + i].y = (double)(-logl((long double)inv_c));
+  }
+  h[kTabLog].y = 0.0;
+  h[kTabLog + 128].y = kLn2;                    // cancels e ln 2 exactly for u next to 1
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (int j = 0; j <= 256; ++j) {
+    h[kTabTrig + j].x = (double)cosl(pi * (long double)j / 128.0L);
+    h[kTabTrig + j].y = (double)sinl(pi * (long double)j / 128.0L);
+  }
+  for (int j = 0; j <= 256; j += 64) {          // exact values on the axes
+    const int q = j / 64;
+    h[kTabTrig + j].x = (q % 2) ? 0.0 : ((q % 4) ? -1.0 : 1.0);
+    h[kTabTrig + j].y = (q % 2) ? ((q % 4 == 1) ? 1.0 : -1.0) : 0.0;
+  }
+  IMB_CUDA(cudaMemcpyToSymbol(g_normal_tab, h, sizeof(h)));
+  ready = true;
+  return IMB_OK;
+}
+
 int grid_blocks(long long work, int threads, int per_sm) {
   const long long need = (work + threads - 1) / threads;
   const long long cap = (long long)state().sm_count * per_sm;
@@ -442,6 +485,7 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
                    int b_stride, double* out_ne, int rows_ne, double* out_cre, int rows_cre,
                    void* stream_) {
   IMB_TRY(check_init());
+  IMB_TRY(upload_normal_tab());
   cudaStream_t stream = (cudaStream_t)stream_;
   DevGrid g;
   IMB_TRY(make_dev_grid(grid, &g));
