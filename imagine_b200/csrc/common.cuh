@@ -160,22 +160,26 @@ constexpr int kTabTrig = 129;    // 257 entries (cos, sin)(pi j / 128)
 constexpr int kTabSize = 386;
 constexpr double kLn2 = 0.6931471805599453;
 
-// ln(K * 2^-53) for an odd 53-bit integer K (so the argument is in (0, 1))
+// ln(K * 2^-53) for an odd 53-bit integer K (so the argument is in (0, 1)).  Exponent and mantissa
+// come from the exact conversion (double)K (one I2F instead of count-leading-zeros + 64-bit shifts).
+// The coefficients of r^4 .. r^7 are cut to their upper 32 bits so that they encode as FP64
+// immediates (no constant materialisation in the loop); with |r| <= 2^-8 that costs < 2e-19.
 __device__ __forceinline__ double log_u53(unsigned long long K, const double2* __restrict__ tab) {
-  const int p = 63 - __clzll((long long)K);                    // top bit, 0..52
-  const unsigned long long frac = (K << (52 - p)) & 0x000FFFFFFFFFFFFFull;
-  const int i = ((int)(frac >> 44) + 1) >> 1;                  // round((m - 1) 128), 0..128
-  const double m = __longlong_as_double((long long)(frac | 0x3FF0000000000000ull));   // [1, 2)
+  const double dk = (double)K;                                 // exact, K < 2^53
+  const unsigned int hi = (unsigned int)__double2hiint(dk);
+  const unsigned int fh = hi & 0x000FFFFFu;
+  const int i = ((int)(fh >> 12) + 1) >> 1;                    // round((m - 1) 128), 0..128
+  const double m = __hiloint2double((int)(fh | 0x3FF00000u), __double2loint(dk));       // [1, 2)
   const double2 t = tab[kTabLog + i];
   const double r = fma(m, t.x, -1.0);                          // m / c_i - 1 (c_i := 1 / t.x exactly)
-  double q = 0.14285714285714285;
-  q = fma(q, r, -0.16666666666666666);
-  q = fma(q, r, 0.2);
+  double q = __hiloint2double(0x3FC24924, 0);                  // 1/7
+  q = fma(q, r, __hiloint2double((int)0xBFC55555, 0));         // -1/6
+  q = fma(q, r, __hiloint2double(0x3FC99999, 0));              // 1/5
   q = fma(q, r, -0.25);
   q = fma(q, r, 0.3333333333333333);
   q = fma(q, r, -0.5);
   const double lp = fma(r * r, q, r);                          // log1p(r)
-  return fma((double)(p - 53), kLn2, t.y) + lp;                // (e, i) = (-1, 128): exactly 0 + lp
+  return fma((double)((int)(hi >> 20) - 1076), kLn2, t.y) + lp;   // (e, i) = (-1, 128): exactly 0 + lp
 }
 
 // (cos, sin)(pi * K * 2^-52) for an odd 53-bit integer K (angle in (0, 2 pi))
@@ -188,10 +192,24 @@ __device__ __forceinline__ void sincos_u53(unsigned long long K, const double2* 
   const double x = df * 6.975736996017264e-16;                 // pi 2^-52
   const double2 cj = tab[kTabTrig + j];
   const double z = x * x;
-  const double sl = fma(x * z, fma(z, 0.008333333333333333, -0.16666666666666666), x);
-  const double cl = fma(z, fma(z, fma(z, -0.001388888888888889, 0.041666666666666664), -0.5), 1.0);
+  // 1/120 and -1/720 as 32-bit-immediate constants (|x| <= pi/256: < 2e-18)
+  const double sl = fma(x * z, fma(z, __hiloint2double(0x3F811111, 0), -0.16666666666666666), x);
+  const double cl = fma(z, fma(z, fma(z, __hiloint2double((int)0xBF56C16C, 0), 0.041666666666666664), -0.5), 1.0);
   cs = fma(cj.x, cl, -(cj.y * sl));
   sn = fma(cj.y, cl, cj.x * sl);
+}
+
+// sqrt(w) for a positive normal w (here w = -2 ln u in [2e-16, 74]): hardware reciprocal-square-root
+// seed (2^-22), one coupled Goldschmidt step (2^-45), one residual correction; within 1 ulp, and no
+// special-case branch (the compiler's IEEE sequence carries one around every call)
+__device__ __forceinline__ double sqrt_pos(double w) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(w));
+  double g = w * y, h = 0.5 * y;
+  const double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  return fma(fma(-g, g, w), h, g);
 }
 
 __device__ __forceinline__ void philox_normal_pair(unsigned long long seed, uint32_t stream,
@@ -201,7 +219,7 @@ __device__ __forceinline__ void philox_normal_pair(unsigned long long seed, uint
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const unsigned long long k1 = ((unsigned long long)x.x << 20) | (unsigned long long)(x.y >> 12);
   const unsigned long long k2 = ((unsigned long long)x.z << 20) | (unsigned long long)(x.w >> 12);
-  const double r = sqrt(-2.0 * log_u53(2 * k1 + 1, tab));      // u1 = (2 k1 + 1) 2^-53
+  const double r = sqrt_pos(-2.0 * log_u53(2 * k1 + 1, tab));  // u1 = (2 k1 + 1) 2^-53
   double s, c;
   sincos_u53(2 * k2 + 1, tab, s, c);                           // 2 u2 = (2 k2 + 1) 2^-52
   z0 = r * c;
