@@ -139,6 +139,197 @@ __global__ void __launch_bounds__(256) bg_gram_kernel(const __grid_constant__ Ba
     }
 }
 
+// ---- N <= 64: one 64 x 64 output tile per CTA, operands streamed by the TMA engine ------------------
+// The first Gram kernel (bg_gram_kernel, kept for N > 64) runs LDG -> st.shared -> barrier -> DMMA ->
+// barrier per 16 columns and reaches 0.84 TB/s (ncu r01: DMMA pipe 37 %, 17 warps per issue waiting on
+// the loads).  Here raw rows go global -> shared asynchronously: one `cp.async.bulk` (SASS UBLKCP) per
+// row and 32-column tile, completing on an mbarrier, in a ring of GSTAGES tiles; centring (x - mean),
+// the weights and y = U (w o d) are applied to the fragments in registers.  Only the lower-triangular
+// 8 x 8 blocks are computed (36 of 64): warp w of each half takes row blocks {w, 7 - w} = 9 DMMAs per
+// 4 columns for every warp; the two warp halves take alternate k-steps and are summed in fixed order.
+constexpr int GSTAGES = 4;
+constexpr int GTILE = 32;                  // columns per stage
+constexpr int GLD = GTILE + 4;             // shared leading dimension: conflict-free 64-bit fragment loads
+constexpr int GVEC = 3 * GTILE;            // mean | w | d of the tile's columns
+constexpr size_t GRAM64_SMEM = sizeof(double) * ((size_t)GSTAGES * (64 * GLD + GVEC)) + 8 * GSTAGES + 128;
+
+__device__ __forceinline__ void mbar_init(unsigned int bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned int bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned int bar, unsigned int parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+      :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned int dst, const void* src, unsigned int bytes, unsigned int bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// one 32-column tile: this warp's k-steps (alternate ones per warp half), row blocks WQ and 7 - WQ
+template <bool WEIGHTED, int WQ>
+__device__ __forceinline__ void gram64_tile(const double* __restrict__ xs, const double* __restrict__ vs,
+                                            int nc, int N, int half, int fr, int fk, double (&acc0)[4][2],
+                                            double (&acc1)[8][2], double& y0, double& y1) {
+  constexpr int R0 = WQ, R1 = 7 - WQ;
+#pragma unroll
+  for (int ks = 0; ks < GTILE / 8; ++ks) {
+    const int k = 4 * (2 * ks + half) + fk;            // this lane's column of the k-step
+    const bool valid = k < nc;
+    const double mu = vs[k];
+    double f[R1 + 1];
+#pragma unroll
+    for (int q = 0; q <= R1; ++q) f[q] = (valid && 8 * q + fr < N) ? xs[(8 * q + fr) * GLD + k] - mu : 0.0;
+    double a0 = f[R0], a1 = f[R1];
+    if (WEIGHTED) {
+      const double wc = valid ? vs[GTILE + k] : 0.0, dd = valid ? vs[2 * GTILE + k] : 0.0;
+      a0 *= wc; a1 *= wc;
+      y0 = fma(a0, dd, y0);
+      y1 = fma(a1, dd, y1);
+    }
+#pragma unroll
+    for (int q = 0; q <= R0; ++q) dmma884(acc0[q][0], acc0[q][1], a0, f[q]);
+#pragma unroll
+    for (int q = 0; q <= R1; ++q) dmma884(acc1[q][0], acc1[q][1], a1, f[q]);
+  }
+}
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(256, 2) bg_gram64_kernel(const __grid_constant__ BatchPtrs p,
+                                                           const __grid_constant__ BatchWs ws, int N, int m,
+                                                           int cols_per_slice, RowLayout L) {
+  extern __shared__ __align__(128) unsigned char g_smem[];
+  double* sX = reinterpret_cast<double*>(g_smem);                       // [GSTAGES][64][GLD]
+  double* sV = sX + (size_t)GSTAGES * 64 * GLD;                         // [GSTAGES][3][GTILE]
+  const unsigned int bar0 = (unsigned int)__cvta_generic_to_shared(sV + (size_t)GSTAGES * GVEC);
+  const int key = blockIdx.y;
+  const KeyWs& kw = ws.k[key];
+  const double* __restrict__ X = p.sims[key];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = blockIdx.x * cols_per_slice;
+  const int c_end = min(m, c0 + cols_per_slice);
+  const int ntiles = (c_end - c0 + GTILE - 1) / GTILE;
+
+  // rows >= N stay zero for the whole kernel; stale columns of a short last tile must be finite
+  for (int e = tid; e < GSTAGES * (64 * GLD + GVEC); e += 256) sX[e] = 0.0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < GSTAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic writes before async writes
+  __syncthreads();
+
+  // warp 0 issues a tile: 2 rows per lane + the column vectors
+  auto issue = [&](int t) {
+    const int s = t % GSTAGES;
+    const int col = c0 + t * GTILE;
+    const int nc = min(GTILE, c_end - col);
+    const unsigned int bytes = (unsigned int)nc * 8u;
+    const unsigned int bar = bar0 + 8 * s;
+    if (lane == 0) mbar_expect_tx(bar, bytes * (unsigned int)(N + (WEIGHTED ? 3 : 1)));
+    __syncwarp();
+    const unsigned int xs = (unsigned int)__cvta_generic_to_shared(sX + (size_t)s * 64 * GLD);
+    for (int r = lane; r < N; r += 32) bulk_g2s(xs + (unsigned int)r * GLD * 8u, X + L.off(r) + col, bytes, bar);
+    const unsigned int vs = (unsigned int)__cvta_generic_to_shared(sV + (size_t)s * GVEC);
+    if (lane == 0) bulk_g2s(vs, kw.mean + col, bytes, bar);
+    if (WEIGHTED && lane == 1) bulk_g2s(vs + GTILE * 8u, kw.w + col, bytes, bar);
+    if (WEIGHTED && lane == 2) bulk_g2s(vs + 2 * GTILE * 8u, kw.diff + col, bytes, bar);
+  };
+  if (warp == 0)
+    for (int t = 0; t < GSTAGES && t < ntiles; ++t) issue(t);
+
+  const int half = warp >> 2, wq = warp & 3;
+  const int r0 = wq, r1 = 7 - wq;                     // the two row blocks of this warp
+  const int fr = lane >> 2, fk = lane & 3;
+  double acc0[4][2], acc1[8][2];                       // blocks (r0, q <= r0) and (r1, q <= r1)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc0[q][0] = acc0[q][1] = 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc1[q][0] = acc1[q][1] = 0.0;
+  double y0 = 0.0, y1 = 0.0;
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t % GSTAGES;
+    mbar_wait(bar0 + 8 * s, (unsigned int)((t / GSTAGES) & 1));
+    const double* xs = sX + (size_t)s * 64 * GLD;
+    const double* vs = sV + (size_t)s * GVEC;
+    const int nc = min(GTILE, c_end - (c0 + t * GTILE));
+    switch (wq) {                                      // row blocks as compile-time constants
+      case 0: gram64_tile<WEIGHTED, 0>(xs, vs, nc, N, half, fr, fk, acc0, acc1, y0, y1); break;
+      case 1: gram64_tile<WEIGHTED, 1>(xs, vs, nc, N, half, fr, fk, acc0, acc1, y0, y1); break;
+      case 2: gram64_tile<WEIGHTED, 2>(xs, vs, nc, N, half, fr, fk, acc0, acc1, y0, y1); break;
+      default: gram64_tile<WEIGHTED, 3>(xs, vs, nc, N, half, fr, fk, acc0, acc1, y0, y1); break;
+    }
+    __syncthreads();                                   // every warp is done with stage s
+    if (warp == 0 && t + GSTAGES < ntiles) issue(t + GSTAGES);
+  }
+
+  // ---- the second warp half hands its sums over; fixed order: half 0 + half 1 ----------------------
+  double* red = sX;                                    // [4 warps][12 blocks][2][32 lanes] + y
+  __syncthreads();
+  if (half == 1) {
+    double* o = red + (size_t)wq * (12 * 64 + 64);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { o[(q * 2) * 32 + lane] = acc0[q][0]; o[(q * 2 + 1) * 32 + lane] = acc0[q][1]; }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { o[((4 + q) * 2) * 32 + lane] = acc1[q][0]; o[((4 + q) * 2 + 1) * 32 + lane] = acc1[q][1]; }
+    o[12 * 64 + lane] = y0; o[12 * 64 + 32 + lane] = y1;
+  }
+  __syncthreads();
+  if (half == 0) {
+    const double* o = red + (size_t)wq * (12 * 64 + 64);
+    double* out = kw.partial + (size_t)blockIdx.x * N * N;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q > r0) continue;
+      const int i = 8 * r0 + fr;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = 8 * q + 2 * fk + h;
+        if (i < N && j < N) out[(size_t)i * N + j] = acc0[q][h] + o[(q * 2 + h) * 32 + lane];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (q > r1) continue;
+      const int i = 8 * r1 + fr;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = 8 * q + 2 * fk + h;
+        if (i < N && j < N) out[(size_t)i * N + j] = acc1[q][h] + o[((4 + q) * 2 + h) * 32 + lane];
+      }
+    }
+    if (WEIGHTED) {
+      y0 += o[12 * 64 + lane]; y1 += o[12 * 64 + 32 + lane];
+      // the 4 lanes of a row hold its 4 k-phases
+      y0 += __shfl_xor_sync(0xffffffffu, y0, 1); y0 += __shfl_xor_sync(0xffffffffu, y0, 2);
+      y1 += __shfl_xor_sync(0xffffffffu, y1, 1); y1 += __shfl_xor_sync(0xffffffffu, y1, 2);
+      if (fk == 0) {
+        if (8 * r0 + fr < N) kw.ypart[(size_t)blockIdx.x * N + 8 * r0 + fr] = y0;
+        if (8 * r1 + fr < N) kw.ypart[(size_t)blockIdx.x * N + 8 * r1 + fr] = y1;
+      }
+    }
+  }
+}
+
+// dst[e] = sum_s partial[s][e] in slice order, upper 8 x 8 blocks mirrored; which = 0 -> G, 1 -> P2
+__global__ void __launch_bounds__(256) bg_reduce64_kernel(const __grid_constant__ BatchWs ws, int nn,
+                                                          int slices, int which, int N) {
+  const KeyWs& kw = ws.k[blockIdx.y];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nn) return;
+  const int i = e / N, j = e % N;
+  const int src = (j / 8 > i / 8) ? j * N + i : e;
+  double s = 0.0;
+  for (int k = 0; k < slices; ++k) s += kw.partial[(size_t)k * nn + src];
+  (which == 0 ? kw.G : kw.P2)[e] = s;
+}
+
 // dst[e] = sum_s partial[s][e] in slice order; which = 0 -> G, 1 -> P2 (Gw section)
 __global__ void __launch_bounds__(256) bg_reduce_kernel(const __grid_constant__ BatchWs ws, int nn,
                                                         int slices, int which, int N) {
@@ -301,6 +492,8 @@ __global__ void __launch_bounds__(256) bg_finish_kernel(const __grid_constant__ 
 // ---- host ---------------------------------------------------------------------------------
 struct BatchCtx {
   int K, N, m, slices, dparts, nn;
+  int cols;        // columns per Gram slice
+  bool use64;      // N <= 64 and 16-byte aligned rows: the TMA-ring Gram kernel
   RowLayout L;
   BatchPtrs p;
   BatchWs ws;
@@ -316,12 +509,18 @@ static int make_ctx(BatchCtx* c, int K, const double* const* sims, int N, int m,
   c->K = K; c->N = N; c->m = m; c->L = L;
   c->nn = N * N;
   c->dparts = grid_blocks(m, 256, 1);
-  c->slices = (m + GCOLS - 1) / GCOLS;
+  // slice width: a function of m only, so a key's summation order never depends on the batch
+  c->use64 = N <= 64 && m % 2 == 0 && L.bstride % 2 == 0 && L.rstride % 2 == 0;
+  for (int k = 0; c->use64 && sims && k < K; ++k)
+    if (reinterpret_cast<uintptr_t>(sims[k]) % 16 != 0) c->use64 = false;
+  c->cols = !c->use64 ? GCOLS : (m >= 32768 ? 1024 : (m >= 8192 ? 512 : GCOLS));
+  c->slices = (m + c->cols - 1) / c->cols;
+  const size_t max_slices = (m + GCOLS - 1) / GCOLS;     // sizing is the same for both kernels
   const size_t nn = c->nn, p2 = nn + N + 4;
   const size_t tn = (size_t)(N + 1) * (N + 1);
-  const size_t partial_elems = (size_t)c->slices * nn > tn ? (size_t)c->slices * nn : tn;
+  const size_t partial_elems = max_slices * nn > tn ? max_slices * nn : tn;
   const size_t per_key = 256 * 12 + sizeof(LikeScalars) +
-                         sizeof(double) * ((size_t)3 * m + partial_elems + nn + p2 + (size_t)c->slices * N +
+                         sizeof(double) * ((size_t)3 * m + partial_elems + nn + p2 + max_slices * N +
                                            4 * (size_t)c->dparts);
   IMB_TRY(ensure_workspace(per_key * K + 512));
   Carver cv(state().ws);
@@ -340,9 +539,20 @@ static int make_ctx(BatchCtx* c, int K, const double* const* sims, int N, int m,
     w.diff = cv.take<double>(m);
     w.w = cv.take<double>(m);
     w.partial = cv.take<double>(partial_elems);
-    w.ypart = cv.take<double>((size_t)c->slices * N);
+    w.ypart = cv.take<double>(max_slices * N);
     w.dpart = cv.take<double>(4 * (size_t)c->dparts);
   }
+  return IMB_OK;
+}
+
+static int gram64_attr() {
+  static bool done = false;
+  if (done) return IMB_OK;
+  IMB_CUDA(cudaFuncSetAttribute(bg_gram64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)GRAM64_SMEM));
+  IMB_CUDA(cudaFuncSetAttribute(bg_gram64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)GRAM64_SMEM));
+  done = true;
   return IMB_OK;
 }
 
@@ -350,6 +560,14 @@ static int phase1(const BatchCtx& c, cudaStream_t s) {
   const int nb = (c.N + TB - 1) / TB;
   bg_colmean_kernel<<<dim3((c.m + 255) / 256, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, c.L);
   IMB_LAUNCHED();
+  if (c.use64) {
+    IMB_TRY(gram64_attr());
+    bg_gram64_kernel<false><<<dim3(c.slices, c.K), 256, GRAM64_SMEM, s>>>(c.p, c.ws, c.N, c.m, c.cols, c.L);
+    IMB_LAUNCHED();
+    bg_reduce64_kernel<<<dim3((c.nn + 255) / 256, c.K), 256, 0, s>>>(c.ws, c.nn, c.slices, 0, c.N);
+    IMB_LAUNCHED();
+    return IMB_OK;
+  }
   bg_gram_kernel<false><<<dim3(c.slices, nb * nb, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, GCOLS, c.L);
   IMB_LAUNCHED();
   bg_reduce_kernel<<<dim3((c.nn + 255) / 256, c.K), 256, 0, s>>>(c.ws, c.nn, c.slices, 0, c.N);
@@ -363,12 +581,20 @@ static int phase2(const BatchCtx& c, double m_total, int estimator, cudaStream_t
   IMB_LAUNCHED();
   bg_dvec_kernel<<<dim3(c.dparts, c.K), 256, 0, s>>>(c.p, c.ws, c.m);
   IMB_LAUNCHED();
-  bg_gram_kernel<true><<<dim3(c.slices, nb * nb, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, GCOLS, c.L);
-  IMB_LAUNCHED();
-  bg_reduce_kernel<<<dim3((c.nn + 255) / 256, c.K), 256, 0, s>>>(c.ws, c.nn, c.slices, 1, c.N);
-  IMB_LAUNCHED();
-  bg_wdot_kernel<<<dim3(c.slices, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, GCOLS, c.L);
-  IMB_LAUNCHED();
+  if (c.use64) {                       // Gw and y = U (w o d) in one pass over the maps
+    IMB_TRY(gram64_attr());
+    bg_gram64_kernel<true><<<dim3(c.slices, c.K), 256, GRAM64_SMEM, s>>>(c.p, c.ws, c.N, c.m, c.cols, c.L);
+    IMB_LAUNCHED();
+    bg_reduce64_kernel<<<dim3((c.nn + 255) / 256, c.K), 256, 0, s>>>(c.ws, c.nn, c.slices, 1, c.N);
+    IMB_LAUNCHED();
+  } else {
+    bg_gram_kernel<true><<<dim3(c.slices, nb * nb, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, GCOLS, c.L);
+    IMB_LAUNCHED();
+    bg_reduce_kernel<<<dim3((c.nn + 255) / 256, c.K), 256, 0, s>>>(c.ws, c.nn, c.slices, 1, c.N);
+    IMB_LAUNCHED();
+    bg_wdot_kernel<<<dim3(c.slices, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, GCOLS, c.L);
+    IMB_LAUNCHED();
+  }
   bg_pack2_kernel<<<c.K, 256, 0, s>>>(c.ws, c.N, c.slices, c.dparts);
   IMB_LAUNCHED();
   return IMB_OK;
