@@ -147,8 +147,14 @@ __global__ void __launch_bounds__(256) bg_gram_kernel(const __grid_constant__ Ba
 // the weights and y = U (w o d) are applied to the fragments in registers.  Only the lower-triangular
 // 8 x 8 blocks are computed (36 of 64): warp w of each half takes row blocks {w, 7 - w} = 9 DMMAs per
 // 4 columns for every warp; the two warp halves take alternate k-steps and are summed in fixed order.
-constexpr int GSTAGES = 4;
-constexpr int GTILE = 32;                  // columns per stage
+#ifndef IMB_GRAM_STAGES
+#define IMB_GRAM_STAGES 3
+#endif
+#ifndef IMB_GRAM_TILE
+#define IMB_GRAM_TILE 64
+#endif
+constexpr int GSTAGES = IMB_GRAM_STAGES;
+constexpr int GTILE = IMB_GRAM_TILE;       // columns per stage (512-byte row segments: DRAM page locality)
 constexpr int GLD = GTILE + 4;             // shared leading dimension: conflict-free 64-bit fragment loads
 constexpr int GVEC = 3 * GTILE;            // mean | w | d of the tile's columns
 constexpr size_t GRAM64_SMEM = sizeof(double) * ((size_t)GSTAGES * (64 * GLD + GVEC)) + 8 * GSTAGES + 128;
@@ -449,7 +455,7 @@ __global__ void __launch_bounds__(256) bg_finish_kernel(const __grid_constant__ 
   const int tid = threadIdx.x, nt = blockDim.x;
   double* T = use_smem ? smT : kw.partial;           // partial is free again: global scratch
   const double* tail = kw.P2 + (size_t)N * N;
-  if (tid == 0) bad = 0;
+  if (tid == 0) bad = 0x7fffffff;
   const double c = sc->c;
   for (int e = tid; e < N * N; e += nt) {
     const int i = e / N, j = e % N;
@@ -457,11 +463,10 @@ __global__ void __launch_bounds__(256) bg_finish_kernel(const __grid_constant__ 
   }
   for (int r = tid; r < N; r += nt) T[(size_t)N * ldt + r] = tail[r];
   __syncthreads();
-  double ld = 0.0, zz = 0.0;
   for (int k = 0; k < N; ++k) {
-    const double pv = T[(size_t)k * ldt + k];
-    if (tid == 0 && !(pv > 0.0) && bad == 0) bad = k + 1;
-    const double inv = 1.0 / pv;
+    // nothing but the update sits between two barriers: the pivots' logarithms and the z^2 terms are
+    // summed after the loop (column k and z_k = T[N][k] are final once column k - 1 is eliminated)
+    const double inv = 1.0 / T[(size_t)k * ldt + k];
     // rows k+1 .. N (row N = rhs), columns k+1 .. min(i, N-1): warp per row, lanes along columns
     for (int i = k + 1 + (tid >> 5); i <= N; i += (nt >> 5)) {
       const double lik = T[(size_t)i * ldt + k] * inv;
@@ -469,13 +474,22 @@ __global__ void __launch_bounds__(256) bg_finish_kernel(const __grid_constant__ 
       for (int j = k + 1 + (tid & 31); j <= jmax; j += 32)
         T[(size_t)i * ldt + j] -= lik * T[(size_t)j * ldt + k];
     }
-    if (tid == 0) {
-      ld += log(pv);                                 // log|K| = sum log(pivot)
-      const double z = T[(size_t)N * ldt + k];       // z_k = a_Nk / sqrt(pivot)
-      zz += z * z * inv;
-    }
     __syncthreads();
   }
+  // log|K| = sum log(pivot), z^T z = sum z_k^2 / pivot_k: thread t takes k = t, t + nt, ... (fixed order)
+  __shared__ double red[32];
+  double ld = 0.0, zz = 0.0;
+  int first_bad = 0x7fffffff;
+  for (int k = tid; k < N; k += nt) {
+    const double pv = T[(size_t)k * ldt + k], z = T[(size_t)N * ldt + k];
+    if (!(pv > 0.0)) first_bad = min(first_bad, k + 1);
+    ld += log(pv);
+    zz += z * z / pv;
+  }
+  ld = block_sum(ld, red);
+  zz = block_sum(zz, red);
+  atomicMin(&bad, first_bad);
+  __syncthreads();
   if (tid == 0) {
     const double s_quad = tail[N], s_logdet = tail[N + 1];
     const double quad = s_quad - c * zz;
@@ -484,7 +498,7 @@ __global__ void __launch_bounds__(256) bg_finish_kernel(const __grid_constant__ 
     sc->s_quad = s_quad; sc->s_logdet = s_logdet;
     sc->quad = quad; sc->logdet = logdet; sc->sign = sign;
     sc->nonpos = (int)tail[N + 2];
-    sc->info = bad;
+    sc->info = bad == 0x7fffffff ? 0 : bad;
     sc->loglike = -0.5 * (quad + sign * logdet);
   }
 }
