@@ -19,6 +19,8 @@ Field plugins that expose `device_descriptor()` (api/fields.py) are fused into o
 any other `Field` subclass still works -- its `get_data` arrays are uploaded and summed on
 the device.
 """
+import logging
+
 import numpy as np
 
 from . import units as u
@@ -30,6 +32,7 @@ from ..hotpath import PeerExchange, exchange_pixel_shards, gather_rows, shard_bo
 
 FIELD_UNITS = {'magnetic_field': u.microgauss, 'thermal_electron_density': u.cm ** -3}
 _NAMES = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
+log = logging.getLogger(__name__)
 
 
 def _torch():
@@ -70,10 +73,40 @@ class _DeviceFieldEvaluator:
         self.effective_b_stride = 4
         self._bufs = {}
 
-    def evaluate(self, fields, grid, lo, hi):
+    def _evaluate_by_reference(self, sim, fields, grid, lo, hi):
+        """
+        Field lists with DEPENDENCIES: the reference's own `Simulator.prepare_fields`
+        (simulator.py:98-180: dependency sort, string and class dependencies, same-type sum) builds the
+        host fields of every realisation; they are uploaded row by row.  Slow path, exact semantics.
+        """
         torch = _torch()
         n_local = hi - lo
         dg = device_grid(grid)
+        rows = {}
+        for i in range(lo, hi):
+            Simulator.prepare_fields(sim, fields, i)
+            for ftype, data in sim.fields.items():
+                if ftype not in _NAMES:
+                    continue
+                rows.setdefault(ftype, []).append(_host_values(data, FIELD_UNITS.get(ftype)))
+        out = {}
+        for ftype, host_rows in rows.items():
+            host = np.stack(host_rows)
+            if ftype == 'magnetic_field':
+                dev = torch.zeros((n_local, dg.ncell, 4), dtype=torch.float64, device='cuda')
+                dev[:, :, :3] = torch.from_numpy(host.reshape(n_local, dg.ncell, 3)).cuda()
+            else:
+                dev = torch.from_numpy(host.reshape(n_local, dg.ncell)).cuda()
+            out[ftype] = dev
+        self.effective_b_stride = 4
+        return dg, out
+
+    def evaluate(self, fields, grid, lo, hi, sim=None, all_fields=None):
+        torch = _torch()
+        n_local = hi - lo
+        dg = device_grid(grid)
+        if sim is not None and any(getattr(f, 'dependencies_list', None) for f in fields):
+            return self._evaluate_by_reference(sim, all_fields if all_fields is not None else fields, grid, lo, hi)
         descs, seed_rows, foreign = [], [], []
         for f in fields:
             d = descriptor_of(f)
@@ -143,6 +176,7 @@ class B200Simulator(Simulator):
                  rank=0, world=1, group=None, exchange='auto'):
         super().__init__(measurements)
         self.exchange = exchange
+        self.exchange_note = None          # set when 'auto' falls back from the fused NVLink exchange
         self._send = None
         self._peer, self._peer_shape = None, None
         self.los_kwargs = dict(observer=tuple(float(u.value_in(v, u.kpc)) for v in observer),
@@ -261,7 +295,7 @@ class B200Simulator(Simulator):
         lo, hi = shard_bounds(N, self.rank, self.world)
         if self._evaluator is None:
             self._evaluator = _DeviceFieldEvaluator(self.b_stride)
-        dg, dev_fields = self._evaluator.evaluate(fields, self.grid, lo, hi)
+        dg, dev_fields = self._evaluator.evaluate(fields, self.grid, lo, hi, sim=self, all_fields=field_list)
         if self._can_shard_pixels(dev_fields):
             return self._call_pixel_sharded(dg, dev_fields, N, hi - lo)
         maps = self._integrate(dg, dev_fields, hi - lo)
@@ -303,9 +337,12 @@ class B200Simulator(Simulator):
             self._peer_shape = shape
             try:                                   # fused NVLink exchange (hotpath.PeerExchange)
                 self._peer = PeerExchange(shape, self.rank, self.group)
-            except Exception:
+            except Exception as exc:
                 if self.exchange == 'peer':
                     raise
+                self.exchange_note = 'all-to-all: symmetric memory unavailable (%s: %s)' % (type(exc).__name__, exc)
+                if self.rank == 0:
+                    log.warning('B200Simulator exchange fallback -- %s', self.exchange_note)
         if self._peer is not None and tuple(self._peer.recv.shape) == shape:
             recv = self._peer.recv
             views = {key: recv[self.rank, k] for k, key in enumerate(self.observables)}
@@ -395,7 +432,7 @@ class B200TestSimulator(Simulator):
         self.register_ensemble_size(field_list)
         fields = _accepted_fields(self, field_list)
         N = self._ensemble_size
-        dg, dev = _DeviceFieldEvaluator(3).evaluate(fields, self.grid, 0, N)
+        dg, dev = _DeviceFieldEvaluator(3).evaluate(fields, self.grid, 0, N, sim=self, all_fields=field_list)
         sims = Simulations()
         for key in self.observables:
             block = engine.test_simulate(dg, dev['magnetic_field'], dev['thermal_electron_density'], N,

@@ -188,8 +188,6 @@ __device__ __forceinline__ void generic_pair(const FieldArgs& a, unsigned int q,
 // ---- magnetic field, realisation-interleaved layouts ---------------------------------------------
 // Thread = (pair of cells, realisation), realisation fastest; the grid stride is a multiple of the
 // interleave, so realisation and seed are fixed per thread.  Layouts (group = r / RL):
-//   RL 4  (b_stride 16):        out[group][cell][r % 4][x,y,z,0]: the four realisations of a vertex
-//                               share one 128-byte line (los_il4.cu); a warp writes 2 KB contiguous
 //   RL 32 | 16 | 8 (b_stride 3 RL): out[group][cell][component][r % RL]: one coalesced 64-bit load per
 //                               corner component for the lane-per-realisation LOS kernel (los_rl.cu)
 // (Measured and dropped: an 8-wide layout storing (B(cell), B(cell + 1 in z)) pairs so that a z-pair
@@ -215,15 +213,9 @@ __global__ void __launch_bounds__(256) field_b_il_kernel(const __grid_constant__
     }
     const long long c0 = 2ll * q;
     const bool has2 = c0 + 1 < a.g.ncell;
-    if (RL == 4) {
-      double* o = out + (((long long)g * a.g.ncell + c0) * 4 + rl) * 4;
-      *reinterpret_cast<double4*>(o) = make_double4(v[0], v[1], v[2], 0.0);
-      if (has2) *reinterpret_cast<double4*>(o + 16) = make_double4(v[3], v[4], v[5], 0.0);
-    } else {
-      double* o = out + ((long long)g * a.g.ncell + c0) * (3 * RL) + rl;
-      o[0] = v[0]; o[RL] = v[1]; o[2 * RL] = v[2];
-      if (has2) { o[3 * RL] = v[3]; o[4 * RL] = v[4]; o[5 * RL] = v[5]; }
-    }
+    double* o = out + ((long long)g * a.g.ncell + c0) * (3 * RL) + rl;
+    o[0] = v[0]; o[RL] = v[1]; o[2 * RL] = v[2];
+    if (has2) { o[3 * RL] = v[3]; o[4 * RL] = v[4]; o[5 * RL] = v[5]; }
   }
 }
 
@@ -490,8 +482,7 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
   DevGrid g;
   IMB_TRY(make_dev_grid(grid, &g));
   if (!fields || nfields < 0 || n_real < 1) return IMB_EINVAL;
-  if (out_B && b_stride != 3 && b_stride != 4 && b_stride != 16 && b_stride != 24 && b_stride != 48 &&
-      b_stride != 96)
+  if (out_B && b_stride != 3 && b_stride != 4 && b_stride != 24 && b_stride != 48 && b_stride != 96)
     return IMB_EINVAL;
   for (int f = 0; f < nfields; ++f)
     if (field_type(fields[f].kind) < 0) return IMB_EINVAL;
@@ -560,17 +551,16 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
     const uintptr_t addr = reinterpret_cast<uintptr_t>(outs[type]);
     if (type == 0) {
       const long long row_elems = g.ncell * b_stride;
-      if (b_stride >= 16) {
+      if (b_stride >= 24) {
         // realisation-interleaved layouts (see field_b_il_kernel); only meaningful per realisation
-        const int rl = b_stride == 16 ? 4 : b_stride / 3;
+        const int rl = b_stride / 3;
         if (need != n_real || addr % 32 != 0) return IMB_EINVAL;
         if ((g.ncell + 1) / 2 * rl >= (1ll << 32)) return IMB_EUNSUPPORTED;   // 32-bit work index
         const int n_groups = (need + rl - 1) / rl;
         int bx = grid_blocks(((g.ncell + 1) / 2) * rl, 256, 8) / n_groups;
         if (bx < 1) bx = 1;
         const dim3 grid(bx, n_groups);
-        if (rl == 4) field_b_il_kernel<4><<<grid, 256, 0, stream>>>(a, outs[type]);
-        else if (rl == 32) field_b_il_kernel<32><<<grid, 256, 0, stream>>>(a, outs[type]);
+        if (rl == 32) field_b_il_kernel<32><<<grid, 256, 0, stream>>>(a, outs[type]);
         else if (rl == 16) field_b_il_kernel<16><<<grid, 256, 0, stream>>>(a, outs[type]);
         else field_b_il_kernel<8><<<grid, 256, 0, stream>>>(a, outs[type]);
       } else if (b_stride == 3) {

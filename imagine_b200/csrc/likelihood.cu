@@ -150,117 +150,6 @@ __global__ void oas_scalars_kernel(const double* __restrict__ G, int N, int m, i
   }
 }
 
-// D_i = var_i + delta, w_i = 1/D_i; block partials of sum d^2/D, sum log(2 pi |D|), #(D<=0), #(D<0)
-__global__ void __launch_bounds__(256) dvec_kernel(const double* __restrict__ var,
-                                                   const double* __restrict__ diff, int m,
-                                                   const LikeScalars* __restrict__ sc,
-                                                   double* __restrict__ w,
-                                                   double* __restrict__ part /*[grid][4]*/) {
-  __shared__ double red[32];
-  const double delta = sc ? sc->delta : 0.0;
-  Comp q, l;
-  double nonpos = 0.0, neg = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-    const double D = __dadd_rn(var[i], delta);
-    const double wi = 1.0 / D;
-    if (w) w[i] = wi;
-    const double d = diff[i];
-    q.add(__dmul_rn(d, __dmul_rn(wi, d)));
-    l.add(log(__dmul_rn(__dmul_rn(fabs(D), 2.0), 3.141592653589793)));
-    if (!(D > 0.0)) nonpos += 1.0;
-    if (D < 0.0) neg += 1.0;
-  }
-  const double a = block_sum(q.value(), red), b = block_sum(l.value(), red);
-  const double c = block_sum(nonpos, red), d = block_sum(neg, red);
-  if (threadIdx.x == 0) {
-    part[4 * blockIdx.x + 0] = a;
-    part[4 * blockIdx.x + 1] = b;
-    part[4 * blockIdx.x + 2] = c;
-    part[4 * blockIdx.x + 3] = d;
-  }
-}
-
-// y[r] = sum_i (X[r,i]-mu_i) w_i d_i ; one block per realisation
-__global__ void __launch_bounds__(256) wdot_kernel(const double* __restrict__ X, int m,
-                                                   const double* __restrict__ mean,
-                                                   const double* __restrict__ w,
-                                                   const double* __restrict__ diff,
-                                                   double* __restrict__ y) {
-  __shared__ double red[32];
-  const double* row = X + (size_t)blockIdx.x * m;
-  Comp s;
-  for (int i = threadIdx.x; i < m; i += blockDim.x) s.add((row[i] - mean[i]) * w[i] * diff[i]);
-  const double v = block_sum(s.value(), red);
-  if (threadIdx.x == 0) y[blockIdx.x] = v;
-}
-
-// Single-block finish of the Gram route:
-//   K = I + c Gw ; log|2 pi A| = sum log(2 pi D) + log|K| ; quad = sum d^2/D - c y^T K^-1 y
-__global__ void __launch_bounds__(256) gram_finish_kernel(double* __restrict__ Gw, int N,
-                                                          double* __restrict__ y,
-                                                          const double* __restrict__ part,
-                                                          int nparts, LikeScalars* __restrict__ sc) {
-  __shared__ double sh[4];
-  __shared__ int bad;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) {
-    double a = 0, b = 0, c = 0, d = 0;
-    for (int k = 0; k < nparts; ++k) {
-      a += part[4 * k]; b += part[4 * k + 1]; c += part[4 * k + 2]; d += part[4 * k + 3];
-    }
-    sh[0] = a; sh[1] = b; sh[2] = c; sh[3] = d;
-    bad = 0;
-  }
-  __syncthreads();
-  const double c = sc->c;
-  for (int e = tid; e < N * N; e += nt) {
-    const int i = e / N, j = e % N;
-    Gw[e] = (i == j ? 1.0 : 0.0) + c * Gw[e];
-  }
-  __syncthreads();
-  // unblocked right-looking Cholesky of K (lower), in place
-  for (int k = 0; k < N; ++k) {
-    if (tid == 0) {
-      const double p = Gw[(size_t)k * N + k];
-      if (!(p > 0.0)) bad = k + 1;
-      Gw[(size_t)k * N + k] = sqrt(p);
-    }
-    __syncthreads();
-    const double lkk = Gw[(size_t)k * N + k];
-    for (int i = k + 1 + tid; i < N; i += nt) Gw[(size_t)i * N + k] /= lkk;
-    __syncthreads();
-    const int rem = N - k - 1;
-    for (int e = tid; e < rem * rem; e += nt) {
-      const int i = k + 1 + e / rem, j = k + 1 + e % rem;
-      if (j <= i) Gw[(size_t)i * N + j] -= Gw[(size_t)i * N + k] * Gw[(size_t)j * N + k];
-    }
-    __syncthreads();
-  }
-  // forward solve L z = y (z overwrites y), log|K| = 2 sum log L_kk
-  if (tid == 0) {
-    double ld = 0.0, zz = 0.0;
-    for (int k = 0; k < N; ++k) {
-      double s = y[k];
-      for (int j = 0; j < k; ++j) s -= Gw[(size_t)k * N + j] * y[j];
-      s /= Gw[(size_t)k * N + k];
-      y[k] = s;
-      zz += s * s;
-      ld += 2.0 * log(Gw[(size_t)k * N + k]);
-    }
-    const double quad = sh[0] - c * zz;
-    const double logdet = sh[1] + ld;
-    const double sign = (((long long)sh[3]) & 1) ? -1.0 : 1.0;
-    sc->s_quad = sh[0];
-    sc->s_logdet = sh[1];
-    sc->quad = quad;
-    sc->logdet = logdet;
-    sc->sign = sign;
-    sc->nonpos = (int)sh[2];
-    sc->info = bad;
-    sc->loglike = -0.5 * (quad + sign * logdet);
-  }
-}
-
 // EnsembleLikelihoodDiagonal / SimpleLikelihood('variance') / SimpleLikelihood(no cov):
 //   mode 0: v = var + X.var(0); mode 1: v = var; mode 2: no covariance (-1/2 d.d)
 __global__ void __launch_bounds__(256) diag_terms_kernel(const double* __restrict__ var,
@@ -368,61 +257,6 @@ int launch_colvar(const double* X, int N, int m, double* var, cudaStream_t s) {
 int launch_oas_scalars(const double* G, int N, int m, int estimator, LikeScalars* sc, cudaStream_t s) {
   oas_scalars_kernel<<<1, 256, 0, s>>>(G, N, m, estimator, sc);
   IMB_LAUNCHED();
-  return IMB_OK;
-}
-
-struct GramWs {
-  double *mean, *diff, *w, *partial, *G, *y, *part;
-  LikeScalars* sc;
-  int nparts;
-};
-
-int carve_gram(int N, int m, GramWs* g, size_t extra_bytes, Carver* out_carver) {
-  const int slices = gram_slices(m);
-  const int nparts = grid_blocks(m, 256, 2);
-  const size_t need = 256 * 16 + sizeof(double) * ((size_t)3 * m + (size_t)(slices + 1) * N * N + N +
-                                                   4 * (size_t)nparts) + sizeof(LikeScalars) + extra_bytes;
-  IMB_TRY(ensure_workspace(need));
-  Carver c(state().ws);
-  g->sc = c.take<LikeScalars>(1);
-  g->mean = c.take<double>(m);
-  g->diff = c.take<double>(m);
-  g->w = c.take<double>(m);
-  g->partial = c.take<double>((size_t)slices * N * N);
-  g->G = c.take<double>((size_t)N * N);
-  g->y = c.take<double>(N);
-  g->part = c.take<double>(4 * (size_t)nparts);
-  g->nparts = nparts;
-  if (out_carver) *out_carver = c;
-  return IMB_OK;
-}
-
-// Gram route; returns IMB_OK with *fallback = 1 when D has non-positive entries
-int loglike_gram(const double* sims, int N, int m, const double* meas, const double* var,
-                 int estimator, double* out, int32_t* info, int* fallback, cudaStream_t s) {
-  GramWs g;
-  IMB_TRY(carve_gram(N, m, &g, 0, nullptr));
-  const int cb = grid_blocks(m, 256, 4);
-  colmean_kernel<<<cb, 256, 0, s>>>(sims, N, m, meas, g.mean, g.diff);
-  IMB_LAUNCHED();
-  IMB_TRY(launch_gram(sims, N, m, g.mean, nullptr, g.partial, g.G, s));
-  oas_scalars_kernel<<<1, 256, 0, s>>>(g.G, N, m, estimator, g.sc);
-  IMB_LAUNCHED();
-  dvec_kernel<<<g.nparts, 256, 0, s>>>(var, g.diff, m, g.sc, g.w, g.part);
-  IMB_LAUNCHED();
-  IMB_TRY(launch_gram(sims, N, m, g.mean, g.w, g.partial, g.G, s));
-  wdot_kernel<<<N, 256, 0, s>>>(sims, m, g.mean, g.w, g.diff, g.y);
-  IMB_LAUNCHED();
-  gram_finish_kernel<<<1, 256, 0, s>>>(g.G, N, g.y, g.part, g.nparts, g.sc);
-  IMB_LAUNCHED();
-  LikeScalars h;
-  IMB_TRY(read_scalars(g.sc, &h, s));
-  *fallback = (h.nonpos > 0 || h.info != 0) ? 1 : 0;
-  *out = h.loglike;
-  if (info) {
-    info[0] = IMB_INFO_ROUTE_GRAM | IMB_INFO_CHOLESKY;
-    info[1] = h.info;
-  }
   return IMB_OK;
 }
 

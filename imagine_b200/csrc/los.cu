@@ -15,7 +15,6 @@
 namespace imb {
 
 int make_dev_grid(const imb_grid* grid, DevGrid* g);
-int launch_los_il4s(const LosArgs& a, bool has_ne, bool has_cre, bool var_p, cudaStream_t s);
 int launch_los_rl(const LosArgs& a, int rl, bool has_ne, bool has_cre, bool var_p, cudaStream_t s);
 
 template <bool HAS_NE, bool HAS_CRE, bool VAR_P, int RT, int BS>
@@ -166,198 +165,6 @@ __global__ void __launch_bounds__(256) los_kernel(const __grid_constant__ LosArg
   }
 }
 
-// ---- realisation-interleaved layout (b_stride 16): B[group][cell][4 realisations][4] -----------
-// A warp = one pixel x 8 consecutive radial samples x 4 realisations of one group (lane = 4*s + r4)
-// and loops over NG groups, so geometry and the shared n_e / CRE interpolants are reused NG times.
-// The four lanes of a sample read the four 32-byte sectors of ONE 128-byte line per corner: a
-// 256-bit gather instruction touches <= 8 lines (4 sectors per L1 wavefront) instead of up to 32
-// with one line per lane in the row-major layouts.
-template <bool HAS_NE, bool HAS_CRE, bool VAR_P, int NG, int MINB>
-__global__ void __launch_bounds__(256, MINB) los_il4_kernel(const __grid_constant__ LosArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int slot = lane >> 2, r4 = lane & 3;
-  const int pix = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (pix >= a.m) return;
-  const int g0 = blockIdx.y * NG;
-  const int n_groups = (a.n_real + 3) >> 2;
-
-  const double nx = __ldg(a.dirs + 3 * pix), ny = __ldg(a.dirs + 3 * pix + 1),
-               nz = __ldg(a.dirs + 3 * pix + 2);
-  const double sth = sqrt(nx * nx + ny * ny);
-  const double cph = sth > 0.0 ? nx / sth : 1.0, sph = sth > 0.0 ? ny / sth : 0.0;
-  const double ex_ = -sph, ey_ = cph;
-  const double nox = -nz * cph, noy = -nz * sph, noz = sth;
-
-  double tmin = 0.0, tmax = a.dr * (double)a.n_steps;
-  {
-    const double nn[3] = {nx, ny, nz};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double lo = a.g.lo[k], hi = lo + (double)(a.g.n[k] - 1) / a.g.inv_step[k];
-      if (nn[k] != 0.0) {
-        const double t1 = (lo - a.obs[k]) / nn[k], t2 = (hi - a.obs[k]) / nn[k];
-        tmin = fmax(tmin, fmin(t1, t2));
-        tmax = fmin(tmax, fmax(t1, t2));
-      } else if (a.obs[k] < lo || a.obs[k] > hi) {
-        tmax = -1.0;
-      }
-    }
-  }
-  int j_lo = 0, j_hi = -1;
-  if (tmax >= tmin) {
-    j_lo = max(0, (int)floor(tmin / a.dr - 0.5) - 1);
-    j_hi = min(a.n_steps - 1, (int)ceil(tmax / a.dr - 0.5) + 1);
-  }
-
-  double accI[NG], accQ[NG], accU[NG], carry[NG], accDM[NG];
-#pragma unroll
-  for (int t = 0; t < NG; ++t) accI[t] = accQ[t] = accU[t] = carry[t] = accDM[t] = 0.0;
-
-  const long long sy = a.g.n[2], sx = (long long)a.g.n[1] * a.g.n[2];
-  const double umx = (double)(a.g.n[0] - 1), umy = (double)(a.g.n[1] - 1),
-               umz = (double)(a.g.n[2] - 1);
-  const long long group_stride = a.g.ncell * 16;
-
-  for (int jb = j_lo; jb <= j_hi; jb += 8) {
-    const int j = jb + slot;
-    const double r = __dmul_rn((double)j + 0.5, a.dr);
-    const double px = __dadd_rn(a.obs[0], __dmul_rn(r, nx));
-    const double py = __dadd_rn(a.obs[1], __dmul_rn(r, ny));
-    const double pz = __dadd_rn(a.obs[2], __dmul_rn(r, nz));
-    double ux = __dmul_rn(__dsub_rn(px, a.g.lo[0]), a.g.inv_step[0]);
-    double uy = __dmul_rn(__dsub_rn(py, a.g.lo[1]), a.g.inv_step[1]);
-    double uz = __dmul_rn(__dsub_rn(pz, a.g.lo[2]), a.g.inv_step[2]);
-    const bool inside = (j <= j_hi) && ux >= 0.0 && ux <= umx && uy >= 0.0 && uy <= umy &&
-                        uz >= 0.0 && uz <= umz;
-    if (!inside) ux = uy = uz = 0.0;
-    const int ix = min((int)ux, a.g.n[0] - 2), iy = min((int)uy, a.g.n[1] - 2),
-              iz = min((int)uz, a.g.n[2] - 2);
-    Cell c;
-    c.base = ((long long)ix * a.g.n[1] + iy) * a.g.n[2] + iz;
-    c.sy = sy; c.sx = sx;
-    c.tx = ux - (double)ix; c.ty = uy - (double)iy; c.tz = uz - (double)iz;
-
-    double kp = a.sync_k, pif = a.pol_frac, expo = a.expo;
-    if (HAS_CRE && VAR_P) {
-      const double R = sqrt(px * px + py * py);
-      const double p = a.alpha - a.beta * R - a.theta * pz;
-      kp = sync_coeff_var(a, p);
-      pif = (p + 1.0) / (p + 7.0 / 3.0);
-      expo = (p + 1.0) * 0.25;
-    }
-
-    double ne_s = 0.0, cre_s = 0.0;
-    const bool ne_shared = HAS_NE && a.ne_row == 0, cre_shared = HAS_CRE && a.cre_row == 0;
-    if (ne_shared) ne_s = inside ? interp_scalar(a.ne, c) : 0.0;
-    if (cre_shared) cre_s = inside ? interp_scalar(a.cre, c) : 0.0;
-
-#pragma unroll
-    for (int t = 0; t < NG; ++t) {
-      const int g = g0 + t;
-      if (g >= n_groups) break;
-      const int rr = g * 4 + r4;
-      const bool live = inside && rr < a.n_real;
-      double bx = 0.0, by = 0.0, bz = 0.0;
-      if (live) {
-        // corner (a,b,c) of this lane's realisation: ((cell)*4 + r4)*4 doubles into the group
-        const double* p = a.B + group_stride * g + c.base * 16 + r4 * 4;
-        const double4 v000 = ldg256(p), v001 = ldg256(p + 16);
-        const double4 v010 = ldg256(p + c.sy * 16), v011 = ldg256(p + c.sy * 16 + 16);
-        const double4 v100 = ldg256(p + c.sx * 16), v101 = ldg256(p + c.sx * 16 + 16);
-        const double4 v110 = ldg256(p + (c.sx + c.sy) * 16), v111 = ldg256(p + (c.sx + c.sy) * 16 + 16);
-        bx = lerp(lerp(lerp(v000.x, v001.x, c.tz), lerp(v010.x, v011.x, c.tz), c.ty),
-                  lerp(lerp(v100.x, v101.x, c.tz), lerp(v110.x, v111.x, c.tz), c.ty), c.tx);
-        by = lerp(lerp(lerp(v000.y, v001.y, c.tz), lerp(v010.y, v011.y, c.tz), c.ty),
-                  lerp(lerp(v100.y, v101.y, c.tz), lerp(v110.y, v111.y, c.tz), c.ty), c.tx);
-        bz = lerp(lerp(lerp(v000.z, v001.z, c.tz), lerp(v010.z, v011.z, c.tz), c.ty),
-                  lerp(lerp(v100.z, v101.z, c.tz), lerp(v110.z, v111.z, c.tz), c.ty), c.tx);
-      }
-      double phi = 0.0;
-      if (HAS_NE) {
-        if (!ne_shared) ne_s = live ? interp_scalar(a.ne + a.ne_row * rr, c) : 0.0;
-        const double bpar = -(bx * nx + by * ny + bz * nz);
-        const double f = __dmul_rn(__dmul_rn(__dmul_rn(0.812, ne_s), bpar), a.dl_pc);
-        double x = f;
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {      // inclusive scan over the 8 samples of this realisation
-          const double up = __shfl_up_sync(0xffffffffu, x, o);
-          if (lane >= o) x += up;
-        }
-        phi = (carry[t] + x) - 0.5 * f;
-        carry[t] += __shfl_sync(0xffffffffu, x, 28 + r4);
-        accDM[t] += ne_s * a.dl_pc;
-      }
-      if (HAS_CRE) {
-        if (!cre_shared) cre_s = live ? interp_scalar(a.cre + a.cre_row * rr, c) : 0.0;
-        const double bn = bx * nox + by * noy + bz * noz;
-        const double be = bx * ex_ + by * ey_;
-        const double bp2 = bn * bn + be * be;
-        if (bp2 > 0.0) {
-          const double pw = (expo == 1.0) ? bp2 : pow(bp2, expo);
-          const double em = cre_s * kp * pw * a.dl_cm;
-          const double gq = -em * pif / bp2;
-          const double qc = gq * (bn * bn - be * be), uc = gq * (2.0 * bn * be);
-          accI[t] += em;
-          if (HAS_NE) {
-            double sa, ca;
-            sincos(2.0 * phi * a.lam2, &sa, &ca);
-            accQ[t] += qc * ca - uc * sa;
-            accU[t] += qc * sa + uc * ca;
-          } else {
-            accQ[t] += qc;
-            accU[t] += uc;
-          }
-        }
-      }
-    }
-  }
-
-#pragma unroll
-  for (int t = 0; t < NG; ++t) {
-    const int g = g0 + t;
-    if (g >= n_groups) break;
-    const int rr = g * 4 + r4;
-    double dm = accDM[t], I = accI[t], Q = accQ[t], U = accU[t];
-#pragma unroll
-    for (int o = 4; o < 32; o <<= 1) {
-      if (HAS_NE) dm += __shfl_xor_sync(0xffffffffu, dm, o);
-      if (HAS_CRE) {
-        I += __shfl_xor_sync(0xffffffffu, I, o);
-        Q += __shfl_xor_sync(0xffffffffu, Q, o);
-        U += __shfl_xor_sync(0xffffffffu, U, o);
-      }
-    }
-    if (slot == 0 && rr < a.n_real) {
-      const long long o = out_index(a, rr, pix);
-      if (HAS_NE) {
-        if (a.out_dm) a.out_dm[o] = dm;
-        if (a.out_fd) a.out_fd[o] = carry[t];
-      }
-      if (HAS_CRE) {
-        if (a.out_I) a.out_I[o] = I;
-        if (a.out_Q) a.out_Q[o] = Q;
-        if (a.out_U) a.out_U[o] = U;
-      }
-    }
-  }
-}
-
-template <bool HAS_NE, bool HAS_CRE, bool VAR_P>
-static void launch_il4(const LosArgs& a, cudaStream_t s) {
-  const int warps = 8;
-  const int n_groups = (a.n_real + 3) / 4;
-  int ng = n_groups >= 4 ? 4 : (n_groups >= 2 ? 2 : 1);
-  int minb = 2;
-  if (const char* e = getenv("IMB_LOS_NG")) ng = atoi(e);
-  if (const char* e = getenv("IMB_LOS_MINB")) minb = atoi(e);
-  dim3 grid((a.m + warps - 1) / warps, (n_groups + ng - 1) / ng);
-#define IMB_IL4(NG_, MB_) los_il4_kernel<HAS_NE, HAS_CRE, VAR_P, NG_, MB_><<<grid, 256, 0, s>>>(a)
-  if (ng == 4) { if (minb >= 3) IMB_IL4(4, 3); else if (minb == 1) IMB_IL4(4, 1); else IMB_IL4(4, 2); }
-  else if (ng == 2) { if (minb >= 4) IMB_IL4(2, 4); else if (minb == 3) IMB_IL4(2, 3); else if (minb == 1) IMB_IL4(2, 1); else IMB_IL4(2, 2); }
-  else { if (minb >= 4) IMB_IL4(1, 4); else if (minb == 3) IMB_IL4(1, 3); else IMB_IL4(1, 2); }
-#undef IMB_IL4
-}
-
 template <bool HAS_NE, bool HAS_CRE, bool VAR_P, int RT>
 static void launch_bs(const LosArgs& a, int bs, dim3 grid, cudaStream_t s) {
   if (bs == 4) los_kernel<HAS_NE, HAS_CRE, VAR_P, RT, 4><<<grid, 256, 0, s>>>(a);
@@ -401,10 +208,10 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
   IMB_TRY(make_dev_grid(grid, &a.g));
   if (m == 0 && cfg && n_real >= 1) return IMB_OK;            // nothing to integrate
   if (!cfg || !dirs || !B || m < 0 || n_real < 1) return IMB_EINVAL;
-  if (b_stride != 3 && b_stride != 4 && b_stride != 16 && b_stride != 24 && b_stride != 48 && b_stride != 96)
+  if (b_stride != 3 && b_stride != 4 && b_stride != 24 && b_stride != 48 && b_stride != 96)
     return IMB_EINVAL;
   if (b_stride >= 4 && (reinterpret_cast<uintptr_t>(B) % 32 != 0)) return IMB_EINVAL;
-  if (b_stride >= 16 && rows_B != n_real) return IMB_EINVAL;   // interleaved layouts are per realisation
+  if (b_stride >= 24 && rows_B != n_real) return IMB_EINVAL;   // interleaved layouts are per realisation
   for (int k = 0; k < 3; ++k)
     if (grid->n[k] < 2 || !(grid->hi[k] > grid->lo[k])) return IMB_EINVAL;  // trilinear needs a cell
   if (cfg->n_steps < 0 || !(cfg->dr > 0.0)) return IMB_EINVAL;
@@ -462,7 +269,7 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
     a.n_peers = cfg->n_peers;
     for (int d = 0; d < cfg->n_peers; ++d) a.peer_delta[d] = cfg->peer_delta[d];
   }
-  if (b_stride >= 16 && has_ne && has_cre && rows_ne == 1 && rows_cre == 1) {
+  if (b_stride >= 24 && has_ne && has_cre && rows_ne == 1 && rows_cre == 1) {
     // pack the two shared scalar grids into (n_e, CRE) pairs: one 128-bit gather per vertex
     IMB_TRY(ensure_buffer(&state().aux, &state().aux_bytes, sizeof(double) * 2 * (size_t)a.g.ncell));
     double* packed = static_cast<double*>(state().aux);
@@ -471,7 +278,13 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
     a.necre = packed;
   }
 
-  // realisation tile: reuse geometry + deterministic interpolants across realisations
+  cudaStream_t s = (cudaStream_t)stream;
+  if (b_stride >= 24) {                       // lane = realisation (los_rl.cu); always one row per realisation
+    IMB_TRY(launch_los_rl(a, b_stride / 3, has_ne, has_cre, var_p, s));
+    IMB_LAUNCHED();
+    return IMB_OK;
+  }
+  // row-major interchange layouts: realisation tile, reuse geometry + deterministic interpolants
   int rt = 1;
   const bool per_real = rows_B > 1 || rows_ne > 1 || rows_cre > 1;
   if (!per_real && cfg->out_cols_per_dest > 0) return IMB_EUNSUPPORTED;
@@ -480,30 +293,6 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
     a.n_real = 1;
   } else {
     rt = n_real >= 4 ? 4 : (n_real >= 2 ? 2 : 1);
-  }
-  cudaStream_t s = (cudaStream_t)stream;
-  if (b_stride == 24 || b_stride == 48 || b_stride == 96) {     // lane = realisation (los_rl.cu)
-    IMB_TRY(launch_los_rl(a, b_stride / 3, has_ne, has_cre, var_p, s));
-    IMB_LAUNCHED();
-    return IMB_OK;
-  }
-  if (b_stride == 16 && !getenv("IMB_LOS_REGISTER_ACC")) {
-    IMB_TRY(launch_los_il4s(a, has_ne, has_cre, var_p, s));
-    IMB_LAUNCHED();
-    return IMB_OK;
-  }
-  if (b_stride == 16) {      // first interleaved kernel (register accumulators), kept for A/B runs
-    if (has_ne && has_cre) {
-      if (var_p) launch_il4<true, true, true>(a, s);
-      else launch_il4<true, true, false>(a, s);
-    } else if (has_ne) {
-      launch_il4<true, false, false>(a, s);
-    } else {
-      if (var_p) launch_il4<false, true, true>(a, s);
-      else launch_il4<false, true, false>(a, s);
-    }
-    IMB_LAUNCHED();
-    return IMB_OK;
   }
   if (has_ne && has_cre) {
     if (var_p) launch_rt<true, true, true>(a, b_stride, rt, s);

@@ -80,23 +80,21 @@ def field_rows(descs, n_real):
 FIELD_NAMES = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
 
 
-INTERLEAVED_STRIDES = (16, 24, 48, 96)
+INTERLEAVED_STRIDES = (24, 48, 96)
 
 
 def pick_b_stride(n_real):
     """Widest realisation interleave a block of `n_real` realisations fills without padding:
-    96 / 48 / 24 = [group][cell][3][32 / 16 / 8] (lane-per-realisation LOS kernel, los_rl.cu), else
-    16 = [group][cell][4][4] (los_il4.cu)."""
+    96 / 48 / 24 = [group][cell][3][32 / 16 / 8] (lane-per-realisation LOS kernel, los_rl.cu); any other
+    count takes the 8-wide layout with the last group padded (idle lanes)."""
     for rl in (32, 16, 8):
         if n_real % rl == 0:
             return 3 * rl
-    return 16
+    return 24
 
 
 def b_shape(rows, ncell, b_stride):
     """Shape of the magnetic-field buffer for a layout code."""
-    if b_stride == 16:
-        return ((rows + 3) // 4, ncell, 4, 4)           # [group][cell][realisation % 4][x,y,z,0]
     if b_stride in (24, 48, 96):
         rl = b_stride // 3
         return ((rows + rl - 1) // rl, ncell, 3, rl)    # [group][cell][x|y|z][realisation % RL]
@@ -106,7 +104,7 @@ def b_shape(rows, ncell, b_stride):
 def b_stride_of(B):
     """Layout code of a magnetic-field buffer (inverse of `b_shape`)."""
     if B.dim() == 4:
-        return 16 if tuple(B.shape[-2:]) == (4, 4) else 3 * int(B.shape[-1])
+        return 3 * int(B.shape[-1])
     return int(B.shape[-1])
 
 
@@ -324,10 +322,38 @@ def _ptr_array(ts):
     return (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
 
 
+KMAX_BATCH = 16          # observables per batched launch (gram_batch.cu:KMAX)
+
+
+def _check_key_views(tensors, name):
+    """The phased / asynchronous entry points take raw row pointers (views into exchange buffers are
+    legitimate): every tensor must be CUDA float64 with unit stride along the pixels."""
+    torch = _torch()
+    for t in tensors:
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64):
+            raise TypeError('%s must be CUDA float64 tensors' % name)
+        if t.dim() >= 1 and t.numel() > 0 and t.stride(-1) != 1:
+            raise ValueError('%s must be contiguous along the pixel axis' % name)
+
+
+def _check_out(out, flags, K):
+    torch = _torch()
+    if K < 1 or K > KMAX_BATCH:
+        raise ValueError('between 1 and %d observables per batched call' % KMAX_BATCH)
+    if not (out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.numel() >= K):
+        raise TypeError('out must be a contiguous CUDA float64 tensor with at least K elements')
+    if flags is not None and not (flags.is_cuda and flags.dtype == torch.int32 and flags.is_contiguous()
+                                  and flags.numel() >= K):
+        raise TypeError('flags must be a contiguous CUDA int32 tensor with at least K elements')
+
+
 def gram_phase1(sims, N, m_local, layout, meas, G):
     """imb_gram_phase1: partial Gram of the local pixels of every key into G [K, N, N]."""
     L.init()
     rpb, bstride, rstride = layout
+    _check_key_views(sims, 'sims'); _check_key_views(meas, 'meas'); _check_key_views([G], 'G')
+    if not 1 <= len(sims) <= KMAX_BATCH:
+        raise ValueError('between 1 and %d observables per batched call' % KMAX_BATCH)
     L.check(L.load().imb_gram_phase1(len(sims), _ptr_array(sims), N, m_local, rpb, bstride, rstride,
                                      _ptr_array(meas), L.ptr(G), L.stream_ptr()))
 
@@ -336,6 +362,10 @@ def gram_phase2(sims, N, m_local, layout, meas, var, m_total, G, P2, estimator='
     """imb_gram_phase2: shrinkage from the (all-reduced) G, then the partial P2 [K, N*N+N+4]."""
     L.init()
     rpb, bstride, rstride = layout
+    _check_key_views(sims, 'sims'); _check_key_views(meas, 'meas'); _check_key_views(var, 'var')
+    _check_key_views([G, P2], 'G / P2')
+    if not 1 <= len(sims) <= KMAX_BATCH:
+        raise ValueError('between 1 and %d observables per batched call' % KMAX_BATCH)
     L.check(L.load().imb_gram_phase2(len(sims), _ptr_array(sims), N, m_local, rpb, bstride, rstride,
                                      _ptr_array(meas), _ptr_array(var), int(m_total), _EST[estimator],
                                      L.ptr(G), L.ptr(P2), L.stream_ptr()))
@@ -358,7 +388,14 @@ def loglike_ensemble_batch_async(sims, meas, var, out, flags=None, estimator='oa
     """As `loglike_ensemble_batch`, but values go to the device tensor `out` [K] and nothing syncs."""
     L.init()
     K = len(sims)
+    sims = [_f64(t, 'sims') for t in sims]
+    meas = [_f64(t, 'meas').reshape(-1) for t in meas]
+    var = [_f64(t, 'var').reshape(-1) for t in var]
+    _check_out(out, flags, K)
     N, m = sims[0].shape
+    for s_, y_, v_ in zip(sims, meas, var):
+        if tuple(s_.shape) != (N, m) or y_.numel() != m or v_.numel() != m:
+            raise ValueError('every observable of a batch must have the same [N, m] shape')
     L.check(L.load().imb_loglike_ensemble_batch_async(K, _ptr_array(sims), N, m, _ptr_array(meas),
                                                       _ptr_array(var), _EST[estimator], L.ptr(out),
                                                       L.ptr(flags), L.stream_ptr()))
@@ -367,6 +404,8 @@ def loglike_ensemble_batch_async(sims, meas, var, out, flags=None, estimator='oa
 def gram_phase3_async(K, N, m_local, G, P2, out, flags=None):
     """imb_gram_phase3_async: per-key values into the device tensor `out` [K]; no synchronisation."""
     L.init()
+    _check_key_views([G, P2], 'G / P2')
+    _check_out(out, flags, K)
     L.check(L.load().imb_gram_phase3_async(K, N, m_local, L.ptr(G), L.ptr(P2), L.ptr(out), L.ptr(flags),
                                            L.stream_ptr()))
 

@@ -27,9 +27,13 @@ Two exchange modes between the simulation and the likelihood:
 Either way every rank returns the identical scalar ("copied to all nodes",
 likelihoods/ensemble_likelihood.py:79-80).
 """
+import logging
+
 import numpy as np
 
 from . import engine
+
+log = logging.getLogger(__name__)
 
 LOS_OUTPUT = {'fd': 'fd', 'dm': 'dm', 'I': 'I', 'Q': 'Q', 'U': 'U'}
 
@@ -131,13 +135,20 @@ class EnsembleEvaluator:
             auto = False
         f64 = torch.float64
         self._symm = None
+        self.exchange_note = None                   # why 'auto' did not end up on the fused exchange
+        if auto and not shardable and self.world > 1:
+            self.exchange_note = ('all-gather: %d pixels do not split over %d ranks' % (self.m, self.world)
+                                  if self.m % self.world else 'all-gather: more than 16 ranks')
         if exchange == 'peer':
             try:
                 self._init_peer_buffers(dev)
-            except Exception:
+            except Exception as exc:
                 if not auto:
                     raise
                 exchange = 'alltoall'               # symmetric memory unavailable: NCCL all-to-all
+                self.exchange_note = 'all-to-all: symmetric memory unavailable (%s: %s)' % (type(exc).__name__, exc)
+        if self.exchange_note and self.rank == 0:
+            log.warning('EnsembleEvaluator exchange fallback -- %s', self.exchange_note)
         self.exchange = exchange
         if self.exchange in ('alltoall', 'peer'):
             self.mp = self.m // self.world

@@ -129,9 +129,8 @@ int64_t imb_launch_count(void);
  *              realisation r lives in group r/RL, lane r%RL, and the RL realisations of one
  *              component of one vertex are contiguous: what the lane-per-realisation LOS kernel
  *              reads with one coalesced 64-bit load per corner component (fastest; pick the
- *              widest RL that divides n_real).  Lanes beyond n_real are written as zeros.
- *              b_stride = 16: [ceil(n_real/4), ncell, 4 realisations, 4] -- the four realisations
- *              of a vertex share one 128-byte line as (Bx,By,Bz,0) records (any n_real).
+ *              widest RL that divides n_real, else 24 with a padded last group).  Lanes beyond
+ *              n_real are written as zeros.
  *   out_ne     [rows_ne, ncell]     out_cre  [rows_cre, ncell]
  * A NULL output skips that field type.  Asynchronous.
  */
@@ -166,7 +165,7 @@ int imb_healpix_ring_dirs(int nside, double* dirs, void* stream);
  * Galactic-centric frame).  Replaces Hammurabi.simulate + the hammurabiX run behind it
  * (simulators/hammurabi.py:193-227); numeric definition: oracle/los.py.
  *   B   [rows_B, ncell, b_stride] (b_stride 3 | 4), or one of the interleaved layouts of
- *       imb_field_eval (b_stride 16 | 24 | 48 | 96);   ne [rows_ne, ncell] or NULL   cre [rows_cre, ncell] or NULL
+ *       imb_field_eval (b_stride 24 | 48 | 96);   ne [rows_ne, ncell] or NULL   cre [rows_cre, ncell] or NULL
  *   out_dm, out_fd, out_I, out_Q, out_U  each [n_real, m] or NULL
  * fd/dm need ne; I/Q/U need cre (IMB_EINVAL otherwise).  Asynchronous.
  */

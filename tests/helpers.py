@@ -44,16 +44,12 @@ def oracle_value(case):
 
 
 def b_to_reference_layout(B, n_real, grid_shape):
-    """Device B buffer (b_stride 3 | 4 | interleaved 16 / 48 / 96) -> NumPy [rows, nx, ny, nz, 3]."""
+    """Device B buffer (b_stride 3 | 4 | interleaved 24 / 48 / 96) -> NumPy [rows, nx, ny, nz, 3]."""
     a = B.cpu().numpy()
     if a.ndim == 4 and a.shape[2] == 3:               # [group][cell][x|y|z][realisation % RL]
         g, ncell, _, rl = a.shape
         a = a.transpose(0, 3, 1, 2).reshape(g * rl, ncell, 3)
         assert (a[n_real:] == 0.0).all()
         a = a[:n_real]
-    elif a.ndim == 4:                                 # [group][cell][realisation % 4][x,y,z,0]
-        g, ncell = a.shape[0], a.shape[1]
-        assert (a[..., 3] == 0.0).all()
-        a = a.transpose(0, 2, 1, 3).reshape(g * 4, ncell, 4)[:n_real]
     rows = a.shape[0]
     return a.reshape(rows, *grid_shape, a.shape[-1])[..., :3]

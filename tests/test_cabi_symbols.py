@@ -64,11 +64,11 @@ def test_field_layout_selection_host_only(lib):
     class G:                      # field_shapes only reads ncell
         ncell = 10
     assert [engine.pick_b_stride(n) for n in (256, 64, 32, 48, 16, 8, 24, 12, 4, 1)] == \
-        [96, 96, 96, 48, 48, 24, 24, 16, 16, 16]
-    for bs, rows in ((96, 64), (96, 33), (48, 16), (24, 8), (16, 5), (4, 3), (3, 3)):
+        [96, 96, 96, 48, 48, 24, 24, 24, 24, 24]
+    for bs, rows in ((96, 64), (96, 33), (48, 16), (24, 8), (24, 5), (4, 3), (3, 3)):
         shape = engine.b_shape(rows, G.ncell, bs)
         assert engine.b_stride_of(torch.empty(shape, dtype=torch.float64)) == bs
-        rl = {96: 32, 48: 16, 24: 8, 16: 4}.get(bs)
+        rl = {96: 32, 48: 16, 24: 8}.get(bs)
         if rl:                    # whole groups: lanes beyond `rows` exist and are zero-filled by the kernel
             assert shape[0] * rl >= rows and (shape[0] - 1) * rl < rows
     stochastic = [(_lib.FIELD_CONST_B, [0, 1, 0], 0), (_lib.FIELD_GAUSS_B, [0, 2], 1), (_lib.FIELD_EXP_NE, [.01, 3, .1], 2)]

@@ -63,7 +63,7 @@ def test_tutorial_golden_on_gpu(eng):
     assert np.allclose(got['thermal_electron_density'][0, 3:5, 3:5, 3:5].ravel(), want, rtol=0, atol=5e-9)
 
 
-@pytest.mark.parametrize('bs', [3, 4, 16, 24, 48, 96])
+@pytest.mark.parametrize('bs', [3, 4, 24, 48, 96])
 @pytest.mark.parametrize('res', [[12, 10, 8], [5, 3, 3], [9, 9, 9]])
 def test_philox_gaussian_fields_match_cpu_philox(eng, res, bs):
     """Counter-based Philox: the CPU restatement reproduces the GPU stream (odd and even ncell)."""
