@@ -55,6 +55,21 @@ def ensemble_seeds(n):
     return np.random.randint(1, 1431655765, n).astype(np.uint64)
 
 
+def los_profile_summary(workload, world, n_local):
+    """dram bytes of ONE launch of the committed LOS kernel from its `ncu --set full` capture
+    (profiles/r02_ncu_los_summary.json, written by tools/ncu_summary.py); None when no capture covers
+    this configuration."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_ncu_los_summary.json')) as f:
+            prof = json.load(f)
+    except Exception:
+        return None
+    for entry in prof.get('captures', []):
+        if entry.get('workload') == workload and entry.get('n_gpus') == world and entry.get('n_local') == n_local:
+            return entry
+    return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -110,49 +125,52 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def cpu_reference(workload, budget_s=15.0):
-    """Bounded CPU sample sized for roughly `budget_s` seconds of work on the box's host cores."""
+def cpu_reference(workload):
+    """The fixed bounded CPU sample (oracle/cpu_path.py): same realisations and pixels on every call."""
     from oracle import cpu_path
     w = WORKLOADS[workload]
-    cores = cpu_path.host_cores()
-    n_s = max(1, min(cores, w['n_real']))
-    m = 12 * w['nside'] ** 2
-    # ~1 ms of NumPy work per (pixel, realisation) and core for all five observables
-    target = max(64 * cores, 800.0 * cores * budget_s)
-    frac = min(1.0, target / float(n_s * m))
-    res = cpu_path.time_sample(BOX, [w['G']] * 3, w['nside'], field_descs(w['quantities']),
-                               ensemble_seeds(w['n_real']), LOS_KW, w['n_real'], n_real_sample=n_s,
-                               pixel_fraction=frac, quantities=w['quantities'])
-    return res
+    return cpu_path.time_sample(BOX, [w['G']] * 3, w['nside'], field_descs(w['quantities']),
+                                ensemble_seeds(w['n_real']), LOS_KW, w['n_real'], quantities=w['quantities'])
+
+
+def cpu_baseline_object(res):
+    return {'value': 1.0 / res['seconds_per_eval'], 'unit': 'evals/s', 'cores': res['cores'], 'kind': 'port',
+            'kinds': res['kinds'], 'sample': res['sample'], 'stages_s': res['stages'],
+            'measured_sample_s': res['measured_sample_s'], 'measured_s': res['measured'],
+            'scale_factor': res['scale_factor'], 'extrapolated': res['extrapolated']}
 
 
 def run_reference(args):
-    """--impl reference: the CPU path on the host cores, same metric/config, rank 0 only."""
+    """--impl reference: the CPU path on the host cores, same metric/config, rank 0 only.  Every step
+    times the same fixed sample (about 10 s on 16 cores); the loop stops after --steps samples or ~150 s
+    of wall clock, whichever comes first, and reports how many were timed."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
     times, last = [], None
-    # every step is a bounded sample; the whole --steps/--warmup run is sized for ~3 minutes
-    budget_s = min(20.0, max(1.0, 150.0 / max(1, args.warmup + args.steps)))
     t_run = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        last = cpu_reference(args.workload, budget_s=budget_s)
-        if i >= args.warmup:
+        last = cpu_reference(args.workload)
+        if i >= args.warmup or args.warmup + args.steps <= 1:
             times.append(last['seconds_per_eval'])
-        if time.perf_counter() - t_run > 400 and times:         # hard stop, never hang the driver
+        if time.perf_counter() - t_run > 150 and times:          # bounded run, never hang the driver
             break
     sec = float(np.mean(times))
     value = 1.0 / sec
+    base = cpu_baseline_object(last)
+    base['value'] = value
     line = {
         'impl': 'reference', 'metric': 'ensemble log-likelihood evals/sec', 'value': value,
         'unit': 'evals/s', 'n_gpus': args.gpus, 'steps': len(times), 'warmup': args.warmup,
         'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args.workload, w, 1),
-        'cpu_baseline': {'value': value, 'unit': 'evals/s', 'cores': last['cores'], 'kind': 'port',
-                         'sample': last['sample'], 'stages_s': last['stages']},
+        'cpu_baseline': base,
         'e2e': {'value': value, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'timing_note': ('ms_per_step is the EXTRAPOLATED time of one full evaluation; each timed step ran the '
+                        'bounded sample (cpu_baseline.measured_sample_s seconds of wall clock)'),
+        'run_wall_s': time.perf_counter() - t_run,
     }
     print(json.dumps(line))
 
@@ -179,7 +197,7 @@ def main():
     ap.add_argument('--points', type=int, default=8, help='parameter points per pipelined flush (extra key)')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'peer', 'alltoall', 'allgather'])
     ap.add_argument('--profile-e2e', action='store_true', help='cProfile the plugin-API loop (stderr)')
-    ap.add_argument('--b-stride', default='auto', help="field layout: 'auto' | 16 | 48 | 96 (A/B runs)")
+    ap.add_argument('--b-stride', default='auto', help="field layout: 'auto' | 24 | 48 | 96 (A/B runs)")
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -360,6 +378,7 @@ def main():
         los_bytes = n_loc * 3 * s_bytes + n_det * s_bytes + n_loc * len(quantities) * m * 8
         field_bytes = n_loc * 3 * s_bytes + n_det * s_bytes
         peak, peak_kind = measured_peak_gbs()
+        prof = los_profile_summary(args.workload, world, n_loc)
         los_gbs = los_bytes / (stage[1] * 1e-3) / 1e9
         n_steps = settings.n_steps
         # exact in-box sample count (geometry only)
@@ -379,23 +398,22 @@ def main():
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': workload_config(args.workload, w, world),
             'e2e': {'value': args.steps / (max(e2e_ms, e2e_wall_ms) * 1e-3), 'unit': 'evals/s',
-                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 8 * len(quantities) * 14,
+                    'h2d_bytes_per_step': int(h2d),
+                    # the one read-back of an evaluation: K LikeScalars records (11 doubles + 2 ints each)
+                    'd2h_bytes_per_step': 96 * len(quantities),
                     'ms_per_step': max(e2e_ms, e2e_wall_ms) / args.steps},
             'gpu_launches': int(launches),
             'clocks': clocks,
-            'roofline': {'kernel': 'los_il4s_kernel' if ev.b_stride == 16 else 'los_rl_kernel', 'bound': 'hbm', 'achieved': los_gbs, 'peak': peak,
+            'roofline': {'kernel': 'los_rl_kernel', 'bound': 'hbm', 'achieved': los_gbs, 'peak': peak,
                          'unit': 'GB/s', 'frac': los_gbs / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full:
-                         # profiles/r01_ncu_full_v7.csv (los_rl_kernel) / r01_ncu_full_final.csv
-                         # (los_il4s_kernel); c3 on 1 GPU only
-                         'traffic': ((2910590000 if ev.b_stride == 96 else 3914488000 if ev.b_stride == 16 else None)
-                                     if (args.workload == 'c3' and world == 1) else None),
-                         'limiter': ('not HBM at this size: L1 data pipe ~70 % busy (48 wavefronts of corner loads '
-                                     '+ 20 of shared-memory broadcasts per step), 45 % of stall samples wait on '
-                                     'the corner gathers; the B grid leaves HBM once (DRAM 12 % busy)'
-                                     if ev.b_stride != 16 else
-                                     'L1 data-pipe wavefronts of the trilinear gathers (86 % of peak); '
-                                     'the padded B grid leaves HBM once (DRAM 8 % busy)'),
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the committed kernel
+                         'traffic': prof['dram_bytes'] if prof else None,
+                         'traffic_source': (prof['source'] if prof else
+                                            'no ncu capture for this configuration under profiles/'),
+                         'limiter': ('not HBM at this size: the B grid leaves HBM about once (see traffic); the '
+                                     'march is bound by FP64 issue (60 FP64 instructions per sample) and the '
+                                     'latency of the vertex loads at 20 warps / SM; L1 global-load sectors '
+                                     '0.86e9 per launch after the cell-resident rewrite (2.04e9 before)'),
                          'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)',
                          'algorithmic_bytes_per_launch': int(los_bytes),
                          'ms_per_launch': stage[1]},
@@ -407,14 +425,12 @@ def main():
                                   'in_box': n_loc * inbox / (stage[1] * 1e-3),
                                   'in_box_per_realisation': inbox},
             'loglike': float(loglike),
+            'exchange': {'mode': ev.exchange, 'note': ev.exchange_note},
             'pipelined': pipelined,
         }
         if not args.no_cpu_baseline:
             try:
-                res = cpu_reference(args.workload, budget_s=15.0)
-                line['cpu_baseline'] = {'value': 1.0 / res['seconds_per_eval'], 'unit': 'evals/s',
-                                        'cores': res['cores'], 'kind': 'port', 'sample': res['sample'],
-                                        'stages_s': res['stages']}
+                line['cpu_baseline'] = cpu_baseline_object(cpu_reference(args.workload))
             except Exception as exc:                                      # never lose the GPU line
                 line['cpu_baseline'] = {'value': None, 'unit': 'evals/s', 'cores': 0, 'kind': 'port',
                                         'sample': 'failed: %r' % (exc,)}
