@@ -341,3 +341,100 @@ def test_config1_basic_pipeline_shapes(api):
     assert abs(got - want) <= 1e-8 * max(1.0, abs(want))
     assert lik(sim(fields(3.0, 6.0))) == got                      # same seeds, same answer
     assert lik(sim(fields(-4.0, 2.5))) != got
+
+
+# ------------------------------------------------------------ cross-checks against the reference's OWN classes
+def test_reference_likelihoods_agree_on_gpu_simulated_maps(api):
+    """GPU simulator -> DeviceObservable -> the reference's EnsembleLikelihood / Diagonal / Simple classes
+    (unmodified, imagine.likelihoods) and the GPU drop-ins give the same numbers (1e-8 absolute)."""
+    import imagine.likelihoods as RL
+    nside, N = 4, 6
+    grid, meas, keys, fields, _ = _los_setup(api, nside, N)
+    sims = api.B200Simulator(meas, radial_step=0.2)(fields)
+    for ref_cls, gpu_cls, kw in ((RL.EnsembleLikelihood, api.B200EnsembleLikelihood, {}),
+                                 (RL.EnsembleLikelihoodDiagonal, api.B200EnsembleLikelihoodDiagonal, {}),
+                                 (RL.SimpleLikelihood, api.B200SimpleLikelihood, {})):
+        want, got = ref_cls(meas, **kw)(sims), gpu_cls(meas, **kw)(sims)
+        assert abs(got - want) <= 1e-8, (ref_cls.__name__, got, want)
+
+
+def test_bootstrap_dispersion_matches_the_reference_seed_for_seed(api):
+    """likelihood.py:88-100: np.random.randint resampling; with the same NumPy seed the GPU drop-in draws
+    the same row indices and must give the same value and the same dispersion."""
+    import imagine.likelihoods as RL
+    rng = np.random.default_rng(11)
+    key = ('fd', None, 2, None)
+    M, S = api.Measurements(), api.Simulations()
+    M.append(name=key, data=rng.normal(size=(1, 48)), cov_data=np.full(48, 0.5), otype='HEALPix')
+    S.append(name=key, data=rng.normal(size=(12, 48)), otype='HEALPix')
+    np.random.seed(7)
+    want_v, want_d = RL.EnsembleLikelihood(M, compute_dispersion=True, n_bootstrap=25)(S)
+    np.random.seed(7)
+    got_v, got_d = api.B200EnsembleLikelihood(M, compute_dispersion=True, n_bootstrap=25)(S)
+    assert abs(got_v - want_v) <= 1e-8
+    assert abs(got_d - want_d) <= 1e-8 * max(1.0, want_d)
+
+
+def test_gpu_fields_equal_the_reference_field_classes(api):
+    """Deterministic fields: the reference's own compute_field bodies (basic_fields.py, test_field.py) vs
+    the CUDA kernels, 1e-9 relative; constants exact."""
+    import imagine.fields as RF
+    u = api.units
+    box = [[-15, 15] * u.kpc, [-15, 15] * u.kpc, [-3, 3] * u.kpc]
+    grid = api.UniformGrid(box=box, resolution=[15, 13, 9])
+    pairs = [
+        (api.ConstantMagneticField, RF.ConstantMagneticField,
+         {'Bx': 1.5 * u.microgauss, 'By': -2 * u.microgauss, 'Bz': 0.25 * u.microgauss}),
+        (api.ExponentialThermalElectrons, RF.ExponentialThermalElectrons,
+         {'central_density': 0.03 * u.cm ** -3, 'scale_radius': 3.3 * u.kpc, 'scale_height': 0.7 * u.kpc}),
+        (api.ConstantThermalElectrons, RF.ConstantThermalElectrons, {'ne': 0.02 * u.cm ** -3}),
+        (api.CosThermalElectronDensity, RF.CosThermalElectronDensity,
+         {'n0': 0.5 * u.cm ** -3, 'a': 1.0 * u.rad / u.kpc, 'alpha': 0.1 * u.rad, 'b': 0.5 * u.rad / u.kpc,
+          'beta': 0.2 * u.rad, 'c': 0.25 * u.rad / u.kpc, 'gamma': 0.3 * u.rad}),
+    ]
+    for gpu_cls, ref_cls, params in pairs:
+        got, want = gpu_cls(grid, parameters=params).get_data(), ref_cls(grid, parameters=params).get_data()
+        assert got.unit.is_equivalent(want.unit)
+        g, w = np.asarray(got.to_value(want.unit)), np.asarray(want.value)
+        assert g.shape == w.shape
+        if 'Constant' in gpu_cls.__name__:
+            assert np.array_equal(g, w)
+        else:
+            assert np.allclose(g, w, rtol=1e-9, atol=0), gpu_cls.__name__
+    # stochastic fields match the reference's MT19937 stream in distribution: moments of one realisation
+    ref = RF.NaiveGaussianMagneticField(grid, parameters={'a0': 0.5 * u.microgauss, 'b0': 2 * u.microgauss},
+                                        ensemble_size=1, ensemble_seeds=[3]).get_data(0).value
+    gpu = api.NaiveGaussianMagneticField(grid, parameters={'a0': 0.5 * u.microgauss, 'b0': 2 * u.microgauss},
+                                         ensemble_size=1, ensemble_seeds=[3]).get_data(0).value
+    n = ref.size
+    assert abs(gpu.mean() - 0.5) < 5 * 2 / np.sqrt(n) and abs(ref.mean() - 0.5) < 5 * 2 / np.sqrt(n)
+    assert abs(gpu.std() - 2.0) < 5 * 2 / np.sqrt(2 * n) and abs(ref.std() - 2.0) < 5 * 2 / np.sqrt(2 * n)
+
+
+def test_reference_test_simulator_equals_the_gpu_test_simulator(api):
+    """imagine.simulators.TestSimulator (scipy RegularGridInterpolator, nearest) vs B200TestSimulator on the
+    same reference Field objects (foreign host plugins for the GPU simulator)."""
+    import imagine.fields as RF
+    import imagine.simulators as RS
+    u = api.units
+    grid = api.UniformGrid(box=[[0, 2 * np.pi] * u.kpc, [0, 1] * u.kpc, [0, 1] * u.kpc], resolution=[30, 3, 3])
+    x = np.linspace(0.1, 6.0, 7)
+    coords = {'x': x * u.kpc, 'y': np.full(7, 0.4) * u.kpc, 'z': np.full(7, 0.6) * u.kpc}
+    M = api.Measurements()
+    key = ('test', None, 'tab', None)
+    from imagine.observables import TabularDataset
+    ds = TabularDataset({'v': np.ones(7), 'e': np.full(7, 0.1), 'x': x, 'y': np.full(7, 0.4), 'z': np.full(7, 0.6)},
+                        name='test', data_col='v', err_col='e', x_col='x', y_col='y', z_col='z',
+                        units=u.microgauss * u.cm ** -3)
+    M.append(dataset=ds)
+    key = list(M.keys())[0]
+    fields = [RF.ConstantMagneticField(grid, parameters={'Bx': 10.5 * u.microgauss, 'By': 0.5 * u.microgauss,
+                                                         'Bz': 3 * u.microgauss}, ensemble_size=2),
+              RF.CosThermalElectronDensity(grid, parameters={'n0': 0.5 * u.cm ** -3, 'a': 1.0 * u.rad / u.kpc,
+                                                             'alpha': 0 * u.rad, 'b': 0 * u.rad / u.kpc,
+                                                             'beta': np.pi / 2 * u.rad, 'c': 0 * u.rad / u.kpc,
+                                                             'gamma': np.pi / 2 * u.rad}, ensemble_size=2)]
+    want = RS.TestSimulator(M)(fields)[key].data
+    got = api.B200TestSimulator(M)(fields)[key].data
+    assert got.shape == want.shape == (2, 7)
+    assert np.allclose(got, want, rtol=1e-12, atol=0)

@@ -18,7 +18,7 @@ DESCS = [(3, [0.01, 3.0, 0.5], 0), (0, [0.0, 1.0, 0.0], 1), (1, [0.0, 2.0], 2), 
 N, NSIDE, RES = 16, 8, [24, 24, 12]
 
 
-def _setup(rank, world, exchange):
+def _setup(rank, world, exchange, N=N):
     import torch
     from imagine_b200 import engine
     from imagine_b200.hotpath import EnsembleEvaluator
@@ -73,6 +73,11 @@ def _worker(rank, world, port, queue):
     for exchange in ('peer', 'alltoall', 'allgather'):
         ev, seeds, meas, var = _setup(rank, world, exchange)
         out[exchange] = ev.evaluate(DESCS, seeds, meas, var)
+    # one realisation per rank (ensemble size == world size, which distribute_ensemble allows):
+    # the wide layout pads the single realisation into an 8-lane group
+    for exchange in ('peer', 'allgather'):
+        ev, seeds, meas, var = _setup(rank, world, exchange, N=world)
+        out['tiny_' + exchange] = ev.evaluate(DESCS, seeds, meas, var)
     value, sims = _plugin_value(rank, world)
     out['plugin'] = value
     key = ('sync', 23.0, NSIDE, 'Q')
@@ -93,6 +98,8 @@ def test_two_gpu_paths_match_single_gpu():
     ev, seeds, meas, var = _setup(0, 1, 'allgather')
     want = ev.evaluate(DESCS, seeds, meas, var)
     want_plugin, sims1 = _plugin_value(0, 1)
+    ev2, seeds2, meas2, var2 = _setup(0, 1, 'allgather', N=2)
+    want_tiny = ev2.evaluate(DESCS, seeds2, meas2, var2)
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
         port = s.getsockname()[1]
@@ -111,6 +118,8 @@ def test_two_gpu_paths_match_single_gpu():
         assert abs(out['alltoall'] - want) <= 1e-9 * max(1.0, abs(want))  # different summation order
         assert out['peer'] == out['alltoall']                             # fused NVLink exchange: same data, same kernels
         assert out['plugin_sharded'] == 'ShardedDeviceObservable'
+        for mode in ('tiny_peer', 'tiny_allgather'):
+            assert abs(out[mode] - want_tiny) <= 1e-9 * max(1.0, abs(want_tiny)), mode
         assert abs(out['plugin'] - want_plugin) <= 1e-9 * max(1.0, abs(want_plugin))
         q1 = sims1[('sync', 23.0, NSIDE, 'Q')].data
         assert np.allclose(out['plugin_full_Q'], q1, rtol=1e-9, atol=1e-12 * np.abs(q1).max())
