@@ -175,7 +175,7 @@ def _los_setup(api, nside=4, N=4, res=(20, 18, 12)):
     units = [u.rad / u.m ** 2, u.pc / u.cm ** 3, u.K, u.K, u.K, u.K, u.rad]
     for k, un in zip(keys, units):
         meas.append(name=k, data=rng.normal(size=(1, m)) * un, cov_data=np.ones(m) * un ** 2, otype='HEALPix')
-    seeds_b = [101, 102, 103, 104][:N]
+    seeds_b = list(range(101, 101 + N))
     fields = [
         api.ConstantMagneticField(grid, parameters={'Bx': 0 * u.microgauss, 'By': 1 * u.microgauss,
                                                     'Bz': 0 * u.microgauss}, ensemble_size=N),
