@@ -306,6 +306,26 @@ def main():
                      'value': n_flush * args.points / (float(pip_ms[0]) * 1e-3), 'unit': 'evals/s',
                      'loglike': many[-1]}
 
+    # ---- point-parallel mode (the reference's `_mpi_likelihood` decomposition): every rank
+    # evaluates whole parameter points on its own, one small all-gather of the scalars per batch
+    replicated = None
+    if world > 1 and args.points > 0:
+        pts = [(descs, seeds)] * (world * 2)
+        ev.evaluate_points(pts, meas_d, var_d)
+        barrier()
+        n_batch = max(1, args.steps // 4)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(n_batch):
+            rvals = ev.evaluate_points(pts, meas_d, var_d)
+        r1.record()
+        barrier()
+        rep_ms = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(rep_ms, op=dist.ReduceOp.MAX)
+        replicated = {'points_per_batch': len(pts), 'batches': n_batch,
+                      'value': n_batch * len(pts) / (float(rep_ms[0]) * 1e-3), 'unit': 'evals/s',
+                      'loglike': rvals[-1], 'mode': 'one parameter point per GPU, no data-path collective'}
+
     # ---- end-to-end steps: the plugin API a Pipeline calls (pipelines/pipeline.py:827-852, 905-943):
     # new Field objects per evaluation, Simulator.__call__, Likelihood.__call__; measurements and
     # variances start in HOST memory every step (device caches dropped), result is a host float
@@ -427,6 +447,7 @@ def main():
             'loglike': float(loglike),
             'exchange': {'mode': ev.exchange, 'note': ev.exchange_note},
             'pipelined': pipelined,
+            'point_parallel': replicated,
         }
         if not args.no_cpu_baseline:
             try:

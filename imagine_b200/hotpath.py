@@ -126,6 +126,7 @@ class EnsembleEvaluator:
         self.b_stride = engine.pick_b_stride(self.n_local) if b_stride == 'auto' else int(b_stride)
         self.dirs = engine.healpix_ring_dirs(self.nside)
         self._field_bufs = {}
+        self._local = None                          # world = 1 evaluator of evaluate_points
         dev = self.dirs.device
         shardable = self.world > 1 and self.m % self.world == 0 and self.world <= 16
         if exchange == 'auto':
@@ -304,6 +305,36 @@ class EnsembleEvaluator:
                 t += v
             totals.append(t)
         return totals
+
+    def evaluate_points(self, points, meas, var, estimator='oas'):
+        """
+        Point-parallel evaluation: parameter point i is evaluated ENTIRELY on rank i % world (all N
+        realisations, no data-path collective), every rank then learns every value through one small
+        all-gather -- the decomposition of the reference's MPI mode (`Pipeline._mpi_likelihood`,
+        pipelines/pipeline.py:945-996: the cubes of a batch are spread over the ranks and the results
+        broadcast), which is what fills several GPUs when one evaluation does not.  `points` is the same
+        list on every rank.  Values are bit-identical to `world = 1` evaluations (same kernels, same
+        order); ranks with fewer points than the others just wait in the all-gather.
+        """
+        torch = self.torch
+        if self._local is None:
+            self._local = EnsembleEvaluator(self.grid.box, self.grid.resolution, self.nside, self.settings,
+                                            self.quantities, n_real=self.n_real, rank=0, world=1,
+                                            exchange='allgather')
+        mine = list(range(self.rank, len(points), self.world))
+        per_rank = (len(points) + self.world - 1) // self.world
+        vals = torch.full((per_rank,), float('nan'), dtype=torch.float64, device=self.dirs.device)
+        if mine:
+            vals[:len(mine)] = torch.tensor(self._local.evaluate_many([points[i] for i in mine], meas, var, estimator),
+                                            dtype=torch.float64)
+        if self.world > 1:
+            import torch.distributed as dist
+            allv = torch.empty((self.world, per_rank), dtype=torch.float64, device=self.dirs.device)
+            dist.all_gather_into_tensor(allv, vals, group=self.group)
+        else:
+            allv = vals.reshape(1, -1)
+        host = allv.cpu().tolist()
+        return [host[i % self.world][i // self.world] for i in range(len(points))]
 
     def _allreduce(self, t):
         if self.world > 1:

@@ -61,6 +61,16 @@ def _plugin_value(rank, world):
     return lik(sims), sims
 
 
+def _points(seeds):
+    """Three parameter points (the regular field's strength varies) for the point-parallel mode."""
+    pts = []
+    for by in (0.5, 1.0, 2.0):
+        d = list(DESCS)
+        d[1] = (0, [0.0, by, 0.0], 1)
+        pts.append((d, seeds))
+    return pts
+
+
 def _worker(rank, world, port, queue):
     import torch
     import torch.distributed as dist
@@ -78,6 +88,8 @@ def _worker(rank, world, port, queue):
     for exchange in ('peer', 'allgather'):
         ev, seeds, meas, var = _setup(rank, world, exchange, N=world)
         out['tiny_' + exchange] = ev.evaluate(DESCS, seeds, meas, var)
+    ev, seeds, meas, var = _setup(rank, world, 'allgather')
+    out['points'] = ev.evaluate_points(_points(seeds), meas, var)
     value, sims = _plugin_value(rank, world)
     out['plugin'] = value
     key = ('sync', 23.0, NSIDE, 'Q')
@@ -98,6 +110,7 @@ def test_two_gpu_paths_match_single_gpu():
     ev, seeds, meas, var = _setup(0, 1, 'allgather')
     want = ev.evaluate(DESCS, seeds, meas, var)
     want_plugin, sims1 = _plugin_value(0, 1)
+    want_points = [ev.evaluate(d, sd, meas, var) for d, sd in _points(seeds)]
     ev2, seeds2, meas2, var2 = _setup(0, 1, 'allgather', N=2)
     want_tiny = ev2.evaluate(DESCS, seeds2, meas2, var2)
     with socket.socket() as s:
@@ -118,6 +131,7 @@ def test_two_gpu_paths_match_single_gpu():
         assert abs(out['alltoall'] - want) <= 1e-9 * max(1.0, abs(want))  # different summation order
         assert out['peer'] == out['alltoall']                             # fused NVLink exchange: same data, same kernels
         assert out['plugin_sharded'] == 'ShardedDeviceObservable'
+        assert out['points'] == want_points          # point-parallel mode: whole points per rank, bit-identical
         for mode in ('tiny_peer', 'tiny_allgather'):
             assert abs(out[mode] - want_tiny) <= 1e-9 * max(1.0, abs(want_tiny)), mode
         assert abs(out['plugin'] - want_plugin) <= 1e-9 * max(1.0, abs(want_plugin))
