@@ -11,11 +11,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ_DIR = os.path.join(CSRC, 'build')
 LIB_PATH = os.path.join(HERE, 'libimagine_b200.so')
-SOURCES = ['api.cu', 'fields.cu', 'los.cu', 'los_rl.cu', 'likelihood.cu', 'gram_batch.cu', 'dense.cu']
+SOURCES = ['api.cu', 'fields.cu', 'los.cu', 'los_rl.cu', 'likelihood.cu', 'gram_batch.cu', 'dense.cu', 'comm.cu']
 HEADERS = ['common.cuh', 'linalg.cuh', 'los.cuh', os.path.join('..', '..', 'include', 'imagine_b200.h')]
 ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
 COMPILE_FLAGS = ARCH_FLAGS + ['-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC']
-LINK_FLAGS = ARCH_FLAGS + ['-shared', '-cudart', 'static']
+LINK_FLAGS = ARCH_FLAGS + ['-shared', '-cudart', 'static', '-ldl']
 
 
 def _nvcc():

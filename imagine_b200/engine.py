@@ -384,6 +384,50 @@ def gram_phase3(K, N, m_local, G, P2):
     return [out[k] for k in range(K)]
 
 
+# ---- collectives behind the C ABI (csrc/comm.cu): for hosts without torch.distributed -------------------
+def comm_unique_id():
+    """128-byte NCCL id (bytes); rank 0 creates it, the host ships it to the other ranks."""
+    L.init()
+    buf = (C.c_char * 128)()
+    L.check(L.load().imb_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_init(nranks, rank, unique_id):
+    L.init()
+    buf = (C.c_char * 128).from_buffer_copy(unique_id)
+    L.check(L.load().imb_comm_init(int(nranks), int(rank), buf))
+
+
+def comm_finalize():
+    L.check(L.load().imb_comm_finalize())
+
+
+def allreduce_sum(t):
+    """In-place SUM all-reduce of a CUDA float64 tensor over the library's own communicator."""
+    _check_key_views([t], 'tensor')
+    L.check(L.load().imb_allreduce_sum(L.ptr(t), t.numel(), L.stream_ptr()))
+    return t
+
+
+def loglike_ensemble_sharded(sims, N, m_local, layout, meas, var, m_total, G, P2, estimator='oas'):
+    """imb_loglike_ensemble_sharded: the three Gram phases with their two all-reduces in ONE library call."""
+    L.init()
+    rpb, bstride, rstride = layout
+    K = len(sims)
+    _check_key_views(sims, 'sims'); _check_key_views(meas, 'meas'); _check_key_views(var, 'var')
+    _check_key_views([G, P2], 'G / P2')
+    out, info = (C.c_double * K)(), (C.c_int32 * (2 * K))()
+    L.check(L.load().imb_loglike_ensemble_sharded(K, _ptr_array(sims), N, m_local, rpb, bstride, rstride,
+                                                  _ptr_array(meas), _ptr_array(var), int(m_total),
+                                                  _EST[estimator], L.ptr(G), L.ptr(P2), out, info,
+                                                  L.stream_ptr()))
+    for k in range(K):
+        if info[2 * k + 1] != 0:
+            raise np.linalg.LinAlgError('Gram route not applicable for key %d (info %d)' % (k, info[2 * k + 1]))
+    return [out[k] for k in range(K)]
+
+
 def loglike_ensemble_batch_async(sims, meas, var, out, flags=None, estimator='oas'):
     """As `loglike_ensemble_batch`, but values go to the device tensor `out` [K] and nothing syncs."""
     L.init()

@@ -127,6 +127,7 @@ class EnsembleEvaluator:
         self.dirs = engine.healpix_ring_dirs(self.nside)
         self._field_bufs = {}
         self._local = None                          # world = 1 evaluator of evaluate_points
+        self.library_collectives = False            # True: all-reduces through imb_comm_* instead of torch
         dev = self.dirs.device
         shardable = self.world > 1 and self.m % self.world == 0 and self.world <= 16
         if exchange == 'auto':
@@ -248,12 +249,16 @@ class EnsembleEvaluator:
             layout = (self.n_local, self.K * self.n_local * self.mp, self.mp)
             meas_l = [meas[q][self.plo:self.phi] for q in qs]
             var_l = [var[q][self.plo:self.phi] for q in qs]
-            engine.gram_phase1(sims, self.n_real, self.mp, layout, meas_l, self.G)
-            self._allreduce(self.G)
-            engine.gram_phase2(sims, self.n_real, self.mp, layout, meas_l, var_l, self.m, self.G, self.P2,
-                               estimator=estimator)
-            self._allreduce(self.P2)
-            vals = engine.gram_phase3(self.K, self.n_real, self.mp, self.G, self.P2)
+            if self.library_collectives:           # phases + all-reduces inside the library (csrc/comm.cu)
+                vals = engine.loglike_ensemble_sharded(sims, self.n_real, self.mp, layout, meas_l, var_l, self.m,
+                                                       self.G, self.P2, estimator=estimator)
+            else:
+                engine.gram_phase1(sims, self.n_real, self.mp, layout, meas_l, self.G)
+                self._allreduce(self.G)
+                engine.gram_phase2(sims, self.n_real, self.mp, layout, meas_l, var_l, self.m, self.G, self.P2,
+                                   estimator=estimator)
+                self._allreduce(self.P2)
+                vals = engine.gram_phase3(self.K, self.n_real, self.mp, self.G, self.P2)
         else:
             vals = engine.loglike_ensemble_batch([maps[q] for q in qs], [meas[q] for q in qs],
                                                  [var[q] for q in qs], estimator=estimator)

@@ -248,6 +248,31 @@ int imb_gram_phase3(int K, int N, int m_local, double* G, double* P2, double* ou
                     int32_t* out_info, void* stream);
 
 /*
+ * ---- collectives behind the C ABI (csrc/comm.cu) --------------------------------------------------
+ * For hosts without torch.distributed (the reference's MPI mode: tools/mpi_helper.py, pipelines/
+ * pipeline.py:945-996).  NCCL is dlopen'ed on first use.  Rank 0 calls imb_comm_unique_id, the host
+ * ships the 128 bytes to every rank (MPI_Bcast, file, socket), every rank calls imb_comm_init after
+ * imb_init(device).  imb_allreduce_sum is the in-place SUM all-reduce of doubles on `stream`
+ * (mpi_helper.py:132).  imb_loglike_ensemble_sharded = imb_gram_phase1 -> all-reduce(G) ->
+ * imb_gram_phase2 -> all-reduce(P2) -> imb_gram_phase3 in ONE call: EnsembleLikelihood.call
+ * (likelihoods/ensemble_likelihood.py:68-107) for K keys whose pixels are sharded over the ranks;
+ * arguments as the phase calls; G [K,N,N] and P2 [K,N*N+N+4] are caller-owned device scratch; the
+ * values are replicated on every rank.  IMB_ENOTINIT without a communicator, IMB_EUNSUPPORTED when
+ * libnccl.so.2 cannot be loaded.
+ */
+int imb_comm_unique_id(void* out128);
+int imb_comm_init(int nranks, int rank, const void* unique_id128);
+int imb_comm_finalize(void);
+int imb_comm_size(void);
+int imb_comm_rank(void);
+int imb_allreduce_sum(double* device_buf, int64_t count, void* stream);
+int imb_loglike_ensemble_sharded(int K, const double* const* sims, int N, int m_local,
+                                 int rows_per_block, int64_t block_stride, int64_t row_stride,
+                                 const double* const* meas, const double* const* var, int64_t m_total,
+                                 int estimator, double* G, double* P2, double* out_loglike,
+                                 int32_t* out_info, void* stream);
+
+/*
  * Asynchronous variants (K <= 16): the per-key values land in DEVICE memory (out_device [K]) with
  * flag_device [K] (may be NULL; 0 = ok, non-zero = Gram route not applicable for that key) and the
  * call does not synchronise.  Lets a caller pipeline many parameter points -- UltraNest

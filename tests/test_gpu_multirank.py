@@ -90,6 +90,20 @@ def _worker(rank, world, port, queue):
         out['tiny_' + exchange] = ev.evaluate(DESCS, seeds, meas, var)
     ev, seeds, meas, var = _setup(rank, world, 'allgather')
     out['points'] = ev.evaluate_points(_points(seeds), meas, var)
+    # collectives behind the C ABI: the library's own NCCL communicator (the 128-byte id travels through
+    # torch.distributed here; any host transport would do) runs the phased Gram route in ONE call
+    from imagine_b200 import engine
+    idt = torch.zeros(128, dtype=torch.uint8, device='cuda')
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(engine.comm_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(idt, 0)
+    engine.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
+    ev, seeds, meas, var = _setup(rank, world, 'alltoall')
+    ev.library_collectives = True
+    out['c_abi_collectives'] = ev.evaluate(DESCS, seeds, meas, var)
+    t = torch.full((5,), float(rank + 1), dtype=torch.float64, device='cuda')
+    out['c_abi_allreduce'] = engine.allreduce_sum(t).cpu().tolist()
+    engine.comm_finalize()
     value, sims = _plugin_value(rank, world)
     out['plugin'] = value
     key = ('sync', 23.0, NSIDE, 'Q')
@@ -132,6 +146,8 @@ def test_two_gpu_paths_match_single_gpu():
         assert out['peer'] == out['alltoall']                             # fused NVLink exchange: same data, same kernels
         assert out['plugin_sharded'] == 'ShardedDeviceObservable'
         assert out['points'] == want_points          # point-parallel mode: whole points per rank, bit-identical
+        assert out['c_abi_collectives'] == out['alltoall']      # same phases, NCCL called by the library itself
+        assert out['c_abi_allreduce'] == [3.0] * 5
         for mode in ('tiny_peer', 'tiny_allgather'):
             assert abs(out[mode] - want_tiny) <= 1e-9 * max(1.0, abs(want_tiny)), mode
         assert abs(out['plugin'] - want_plugin) <= 1e-9 * max(1.0, abs(want_plugin))

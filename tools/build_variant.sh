@@ -9,7 +9,7 @@ out=variants; mkdir -p $out
 cs=imagine_b200/csrc
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -c $cs/$src -o $out/${name}_${src%.cu}.o
 objs=""
-for f in api fields los los_rl likelihood gram_batch dense; do
+for f in api fields los los_rl likelihood gram_batch dense comm; do
   if [ "$f.cu" == "$src" ]; then objs="$objs $out/${name}_${src%.cu}.o"; else objs="$objs $cs/build/$f.o"; fi
 done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o $out/lib_$name.so $objs
