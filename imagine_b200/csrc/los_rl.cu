@@ -34,7 +34,11 @@
 // Measured and dropped: L1 prefetch of the lines two steps ahead, by CCTL.PF1 or by a load per line
 // (2.44 / 2.30 vs 2.31 ms: what the prefetch hides it costs in issue slots); prefetching the weights
 // into registers (spills, 5.9 ms); 12 warps / SM at 168 registers (2.70 vs 2.31 ms); first version:
-// 128-thread blocks at 72 registers, two realisation groups per warp.
+// 128-thread blocks at 72 registers, two realisation groups per warp.  A persistent variant whose blocks
+// take adjacent pixels from a per-SM work list (to turn the neighbouring rays' shared vertex lines into L1
+// hits: L1 hit rate is 13 % with one-pixel blocks placed by the hardware scheduler): 2.18 vs 2.05 ms at
+// C3, 5.79 vs 5.67 ms on a C4 shard -- the atomics, the extra barrier and 60 bytes of spills cost more
+// than the L2 round trips they save.
 // Numeric definition: oracle/los.py.
 #include <cstdlib>
 #include <type_traits>
