@@ -333,7 +333,7 @@ class B200Simulator(Simulator):
         m = 12 * int(self.observables[0][2]) ** 2
         mp = m // self.world
         shape = (self.world, K, n_local, mp)
-        if self._peer is None and self.exchange in ('auto', 'peer') and self._peer_shape != shape:
+        if self._peer is None and self.exchange == 'peer' and self._peer_shape != shape:
             self._peer_shape = shape
             try:                                   # fused NVLink exchange (hotpath.PeerExchange)
                 self._peer = PeerExchange(shape, self.rank, self.group)

@@ -19,7 +19,9 @@ Two exchange modes between the simulation and the likelihood:
               receive buffer is NVLink symmetric memory (torch.distributed._symmetric_memory) and
               the kernel's epilogue stores the block of destination rank d straight into rank d's
               buffer (peer stores, `imb_los_cfg.peer_delta`), overlapping the exchange with the
-              ray march; a signal-pad barrier replaces the all-to-all.  'auto' tries this first.
+              ray march; a signal-pad barrier replaces the all-to-all.  On request only: with row-major
+              maps the remote stores of a warp are 32 x 8 bytes and the NCCL all-to-all below is faster
+              (8 B200s, C3: 835 vs 760 evals/s; C4: 66 vs 49).
   'allgather' Every rank receives every realisation's full maps (one all-gather per observable)
               and evaluates the likelihood redundantly; what the plugin API needs, since
               `Simulations` must expose the full [N, m] block.
@@ -131,7 +133,10 @@ class EnsembleEvaluator:
         dev = self.dirs.device
         shardable = self.world > 1 and self.m % self.world == 0 and self.world <= 16
         if exchange == 'auto':
-            exchange = 'peer' if shardable else 'allgather'
+            # measured on 8 B200s (profiles/README.md): local stores + one NCCL all-to-all beat the fused
+            # peer-store exchange (C3: 835 vs 760 evals/s, C4: 66 vs 49) -- with row-major maps a warp's 32
+            # remote stores are 8 bytes each; 'peer' stays available on request
+            exchange = 'alltoall' if shardable else 'allgather'
             auto = True
         else:
             auto = False
