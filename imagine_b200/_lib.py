@@ -18,7 +18,7 @@ IMB_OK, IMB_EINVAL, IMB_ECUDA, IMB_ENOMEM, IMB_ENOTINIT, IMB_EBOUNDS, IMB_ESINGU
 
 # field kinds (include/imagine_b200.h)
 (FIELD_CONST_B, FIELD_GAUSS_B, FIELD_CONST_NE, FIELD_EXP_NE, FIELD_COS_NE, FIELD_RANDOM_NE,
- FIELD_CRE_ANALYTIC, FIELD_CRE_CONST, FIELD_LSA_B) = range(9)
+ FIELD_CRE_ANALYTIC, FIELD_CRE_CONST, FIELD_LSA_B, FIELD_JF12_B) = range(10)
 COV_NONE, COV_VARIANCE, COV_DENSE = range(3)
 EST_EMPIRICAL, EST_OAS, EST_DIAGONAL = range(3)
 ROUTE_AUTO, ROUTE_GRAM, ROUTE_DENSE = range(3)
@@ -39,7 +39,7 @@ class Grid(C.Structure):
 
 class FieldDesc(C.Structure):
     _fields_ = [('kind', C.c_int32), ('stream', C.c_int32), ('seed_row', C.c_int32),
-                ('reserved', C.c_int32), ('p', C.c_double * 8)]
+                ('reserved', C.c_int32), ('p', C.c_double * 24)]
 
 
 class LosCfg(C.Structure):
@@ -47,7 +47,8 @@ class LosCfg(C.Structure):
                 ('out_cols_per_dest', C.c_int32), ('nu_ghz', C.c_double), ('alpha', C.c_double),
                 ('beta', C.c_double), ('theta', C.c_double), ('e0_gev', C.c_double),
                 ('sync_k', C.c_double), ('out_dest_stride', C.c_int64), ('n_peers', C.c_int32),
-                ('reserved', C.c_int32), ('peer_delta', C.c_int64 * 16)]
+                ('reserved', C.c_int32), ('peer_delta', C.c_int64 * 16),
+                ('geometry', C.c_void_p), ('geometry_bytes', C.c_int64)]
 
 
 _P = C.c_void_p
@@ -67,6 +68,8 @@ _SIGNATURES = {
     'imb_los_integrate': (C.c_int, [C.POINTER(Grid), C.POINTER(LosCfg), _P, C.c_int, _P, C.c_int,
                                     C.c_int, _P, C.c_int, _P, C.c_int, C.c_int,
                                     _P, _P, _P, _P, _P, _P]),
+    'imb_los_geometry_bytes': (C.c_int64, [C.c_int, C.c_int]),
+    'imb_los_geometry_build': (C.c_int, [C.POINTER(Grid), C.POINTER(LosCfg), _P, C.c_int, _P, C.c_int64, _P]),
     'imb_pol_derive': (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     'imb_ensemble_mean': (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     'imb_ensemble_var': (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),

@@ -12,7 +12,7 @@ from ._bases import (Field, MagneticField, ThermalElectronDensityField, UniformG
 
 from . import units                                                                    # noqa: F401
 from .device_observable import DeviceObservable, ShardedDeviceObservable                                        # noqa: F401
-from .fields import (CosmicRayElectronDensityField, ConstantMagneticField, NaiveGaussianMagneticField, LSAMagneticField,                # noqa: F401
+from .fields import (CosmicRayElectronDensityField, ConstantMagneticField, NaiveGaussianMagneticField, LSAMagneticField, JF12MagneticField,                # noqa: F401
                      ConstantThermalElectrons, ExponentialThermalElectrons,
                      RandomThermalElectrons, CosThermalElectronDensity,
                      AnalyticCosmicRayElectrons, ConstantCosmicRayElectrons)

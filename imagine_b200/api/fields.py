@@ -137,6 +137,23 @@ class LSAMagneticField(_DeviceFieldMixin, MagneticField):
                 self.R_MAX_KPC]
 
 
+class JF12MagneticField(_DeviceFieldMixin, MagneticField):
+    """
+    Jansson & Farrar (2012) regular Galactic magnetic field evaluated on the grid: the gridded
+    counterpart of the `BregJF12` dummy (fields/hamx/breg_jf12.py:9-39: NAME 'breg_jf12', the same 20
+    parameter names, defaults of `BregJF12Factory`).
+    """
+    NAME = 'breg_jf12'
+    PARAMETER_NAMES = ['b_arm1', 'b_arm2', 'b_arm3', 'b_arm4', 'b_arm5', 'b_arm6', 'b_arm7', 'b_ring',
+                       'h_disk', 'w_disk', 'Bn', 'Bs', 'rn', 'rs', 'wh', 'z0', 'B0_X', 'Xtheta', 'rpc_X', 'r0_X']
+    PARAM_UNITS = ((u.microgauss,) * 8 + (u.kpc, u.kpc, u.microgauss, u.microgauss) + (u.kpc,) * 4
+                   + (u.microgauss, u.deg, u.kpc, u.kpc))
+    KIND = L.FIELD_JF12_B
+    DEFAULTS = {'b_arm1': 0.1, 'b_arm2': 3.0, 'b_arm3': -0.9, 'b_arm4': -0.8, 'b_arm5': -2.0, 'b_arm6': -4.2,
+                'b_arm7': 0.0, 'b_ring': 0.1, 'h_disk': 0.40, 'w_disk': 0.27, 'Bn': 1.4, 'Bs': -1.1, 'rn': 9.22,
+                'rs': 16.7, 'wh': 0.20, 'z0': 5.3, 'B0_X': 4.6, 'Xtheta': 49, 'rpc_X': 4.8, 'r0_X': 2.9}
+
+
 class ConstantThermalElectrons(_DeviceFieldMixin, ThermalElectronDensityField):
     NAME = 'constant_TE'
     PARAMETER_NAMES = ['ne']

@@ -24,7 +24,7 @@ import logging
 import numpy as np
 
 from . import units as u
-from ._bases import Simulator, Simulations
+from ._bases import Simulator, Simulations, Masks
 from .device_observable import DeviceObservable, ShardedDeviceObservable
 from .fields import descriptor_of, device_grid
 from .. import engine
@@ -163,6 +163,9 @@ class B200Simulator(Simulator):
     cre_alpha, cre_beta, cre_theta, cre_E0 : CRE spectrum p = alpha - beta R - theta z at E0 [GeV]
                                         (fields/hamx/cre_analytic.py:19-27)
     rank, world, group : ensemble sharding over torch.distributed ranks (pipeline.py:737-744)
+    masks : Masks or None -- applied INSIDE the simulator like `Hammurabi(measurements, masks=...)`
+               (hammurabi.py:281-325: one identical mask covering every observable): masked pixels are not
+               ray-marched at all and come back as zeros in the full-size maps
     exchange : 'auto' | 'peer' | 'alltoall' | 'allgather' -- how the maps reach the likelihood on several ranks
                (hotpath.py); 'alltoall' returns pixel-sharded observables
     """
@@ -173,8 +176,10 @@ class B200Simulator(Simulator):
 
     def __init__(self, measurements, observer=(-8.3, 0.0, 0.006), radial_step=0.1, radial_max=30.0,
                  cre_alpha=3.0, cre_beta=0.0, cre_theta=0.0, cre_E0=20.6, b_stride='auto',
-                 rank=0, world=1, group=None, exchange='auto'):
+                 rank=0, world=1, group=None, exchange='auto', masks=None):
         super().__init__(measurements)
+        self._kept = {}
+        self.masks = masks
         self.exchange = exchange
         self.exchange_note = None          # set when 'auto' falls back from the fused NVLink exchange
         self._send = None
@@ -188,6 +193,7 @@ class B200Simulator(Simulator):
         self._evaluator = None
         self.rank, self.world, self.group = int(rank), int(world), group
         self._dirs = {}
+        self._geo = {}
         self._row_cache = (None, {})
         for key in self.observables:
             name, freq, nside, tag = key
@@ -198,6 +204,36 @@ class B200Simulator(Simulator):
                     raise ValueError('unrecognised synchrotron tag %r' % (tag,))
                 if freq is None:
                     raise ValueError('synchrotron observables need a frequency')
+
+    # -- masks applied while simulating (hammurabi.py:281-325) -------------------------------------
+    @property
+    def masks(self):
+        return self._masks
+
+    @masks.setter
+    def masks(self, masks):
+        if masks is not None:
+            assert isinstance(masks, Masks)
+            mask_keys = [k for k in masks.keys() if k[0] in self.simulated_quantities]
+            for obs in self.observables:
+                assert obs in mask_keys, 'All observables must be covered by the masks'
+            mask_data = masks[mask_keys[0]].data
+            for k in mask_keys:
+                assert np.array_equal(mask_data, masks[k].data), 'All the masks must be identical'
+        self._masks = masks
+        self._kept = {}
+
+    def _kept_pixels(self, nside):
+        """(indices of the unmasked pixels [int64, device], their directions) for one Nside, or None."""
+        if self._masks is None:
+            return None
+        if nside not in self._kept:
+            torch = _torch()
+            key = next(k for k in self._masks.keys() if k[0] in self.simulated_quantities)
+            keep = np.flatnonzero(np.asarray(self._masks[key].data[0]).astype(bool))
+            idx = torch.from_numpy(keep.astype(np.int64)).cuda()
+            self._kept[nside] = (idx, self._dirs_for(nside).index_select(0, idx).contiguous())
+        return self._kept[nside]
 
     # -- unit handling (hammurabi.py:214-227) ---------------------------------------------------
     @staticmethod
@@ -223,6 +259,15 @@ class B200Simulator(Simulator):
             self._dirs[nside] = engine.healpix_ring_dirs(int(nside))
         return self._dirs[nside]
 
+    def _geometry_for(self, dg, nside, settings, dirs):
+        """Geometry cache of the ray march per Nside (engine.LosGeometry); rebuilt when the grid, the
+        sampling or the (masked) direction set changes."""
+        geo = self._geo.get(nside)
+        if geo is None or not geo.matches(dg, settings, dirs):
+            geo = engine.LosGeometry(dg, settings, dirs)
+            self._geo[nside] = geo
+        return geo
+
     # -- the integrator for a block of realisations --------------------------------------------------
     def _integrate(self, dg, fields, n_real, sharded=None):
         """
@@ -242,6 +287,10 @@ class B200Simulator(Simulator):
         result = {}
         for nside, by_freq in groups.items():
             dirs = self._dirs_for(nside)
+            kept = self._kept_pixels(nside)
+            m_full = dirs.shape[0]
+            if kept is not None:
+                dirs = kept[1]
             freqs = [f for f in by_freq if f is not None]
             plain = by_freq.get(None, [])
             launches = [(f, by_freq[f] + (plain if i == 0 else [])) for i, f in enumerate(freqs)]
@@ -263,16 +312,18 @@ class B200Simulator(Simulator):
                 kw = dict(self.los_kwargs)
                 if freq is not None:
                     kw['nu_ghz'] = freq
+                settings = engine.LosSettings(**kw)
+                geo = self._geometry_for(dg, nside, settings, dirs) if B.dim() == 4 else None
                 if sharded is not None:
                     views, layout = sharded
                     out = {(k[0] if k[0] in ('fd', 'dm') else k[3]): views[k] for k in keys}
-                    engine.los_integrate(dg, engine.LosSettings(**kw), dirs, B, ne,
+                    engine.los_integrate(dg, settings, dirs, B, ne,
                                          cre if want & {'I', 'Q', 'U'} else None, n_real=n_real,
-                                         want=tuple(want), out=out, out_layout=layout)
+                                         want=tuple(want), out=out, out_layout=layout, geometry=geo)
                     continue
-                maps = engine.los_integrate(dg, engine.LosSettings(**kw), dirs, B, ne,
+                maps = engine.los_integrate(dg, settings, dirs, B, ne,
                                             cre if want & {'I', 'Q', 'U'} else None,
-                                            n_real=n_real, want=tuple(want))
+                                            n_real=n_real, want=tuple(want), geometry=geo)
                 derived = None
                 for k in keys:
                     if k[0] in ('fd', 'dm'):
@@ -284,7 +335,12 @@ class B200Simulator(Simulator):
                             derived = engine.pol_derive(maps['Q'], maps['U'])
                         t = derived[0] if k[3] == 'PI' else derived[1]
                     s = self._scale(k)
-                    result[k] = t if s == 1.0 else t * s
+                    t = t if s == 1.0 else t * s
+                    if kept is not None:                   # masked pixels were not marched: zeros
+                        full = torch.zeros((t.shape[0], m_full), dtype=t.dtype, device=t.device)
+                        full.index_copy_(1, kept[0], t)
+                        t = full
+                    result[k] = t
         return result
 
     # -- batched public entry -----------------------------------------------------------------------
@@ -312,7 +368,7 @@ class B200Simulator(Simulator):
 
     # -- pixel-sharded exchange (multi-rank fast path) -------------------------------------------------
     def _can_shard_pixels(self, dev_fields):
-        if self.world <= 1 or self.exchange not in ('auto', 'alltoall', 'peer'):
+        if self.world <= 1 or self.exchange not in ('auto', 'alltoall', 'peer') or self._masks is not None:
             return False
         nsides = {int(k[2]) for k in self.observables}
         direct = all(k[0] in ('fd', 'dm') or k[3] in ('I', 'Q', 'U') for k in self.observables)
@@ -393,6 +449,8 @@ class B200Simulator(Simulator):
     def __getstate__(self):
         state = dict(self.__dict__)
         state['_dirs'] = {}
+        state['_geo'] = {}
+        state['_kept'] = {}
         state['_evaluator'] = None
         state['_send'] = None
         state['_peer'], state['_peer_shape'] = None, None

@@ -25,7 +25,7 @@ struct FieldArgs {
   int kind[IMB_MAX_FIELDS];
   unsigned int stream[IMB_MAX_FIELDS];
   int seed_row[IMB_MAX_FIELDS];
-  double p[IMB_MAX_FIELDS][8];
+  double p[IMB_MAX_FIELDS][24];
   int n_real;                       // seeds row length
   const unsigned long long* seeds;  // device [n_seed_rows, n_real]
   // fast path of the magnetic-field kernels: constant fields followed by ONE Gaussian field (or
@@ -83,6 +83,73 @@ __device__ __forceinline__ void lsa_field(const double* p, double x, double y, d
   b[2] = __dmul_rn(p[0], sin(chi));
 }
 
+// cell pair of a position-dependent regular model
+template <typename F>
+__device__ __forceinline__ void model_pair(const DevGrid& g, const double* p, long long c0, bool has2, double* t,
+                                           F model) {
+  double x, y, z;
+  cell_xyz(g, c0, x, y, z);
+  model(p, x, y, z, t);
+  if (has2) {
+    cell_xyz(g, c0 + 1, x, y, z);
+    model(p, x, y, z, t + 3);
+  } else {
+    t[3] = t[4] = t[5] = 0.0;
+  }
+}
+
+// Jansson & Farrar (2012) regular field (the model hammurabiX's `breg_jf12` implements; the reference
+// only routes its 20 parameters to the binary, fields/hamx/breg_jf12.py:17-39).  Same operations as
+// oracle/fields.py:jf12_B.  p = b_arm1..7, b_ring, h_disk, w_disk, Bn, Bs, rn, rs, wh, z0, B0_X,
+// Xtheta [deg], rpc_X, r0_X.
+__device__ __forceinline__ double jf12_logistic(double v, double h, double w) {
+  return 1.0 / (1.0 + exp(-2.0 * (fabs(v) - h) / w));
+}
+
+__device__ __noinline__ void jf12_field(const double* p, double x, double y, double z, double* b) {
+  const double rc[8] = {5.1, 6.3, 7.1, 8.3, 9.8, 11.4, 12.7, 15.5};
+  const double fa[8] = {0.130, 0.165, 0.094, 0.122, 0.13, 0.118, 0.084, 0.156};
+  const double R = sqrt(x * x + y * y), rsph = sqrt(R * R + z * z);
+  b[0] = b[1] = b[2] = 0.0;
+  if (!(rsph >= 1.0) || !(R <= 20.0) || !(R > 0.0)) return;
+  const double cp = x / R, sp = y / R, phi = atan2(y, x);
+  const double pitch = 11.5 * 0.017453292519943295;
+  const double sin_i = sin(pitch), cos_i = cos(pitch), tan_c = tan(1.5707963267948966 - pitch);
+  double barm[8], s8 = 0.0;
+  for (int i = 0; i < 7; ++i) { barm[i] = p[i]; s8 += fa[i] * p[i]; }
+  barm[7] = -s8 / fa[7];
+  const double lfd = jf12_logistic(z, p[8], p[9]);
+  double r_negx = R * exp(-(phi - 3.141592653589793) / tan_c);
+  if (r_negx > rc[7]) r_negx = R * exp(-(phi + 3.141592653589793) / tan_c);
+  if (r_negx > rc[7]) r_negx = R * exp(-(phi + 3.0 * 3.141592653589793) / tan_c);
+  double arm = 0.0;
+  for (int i = 7; i >= 0; --i) if (r_negx < rc[i]) arm = barm[i];
+  double bdr = 0.0, bdp = 0.0;
+  if (R > 5.0) {
+    const double bm = arm * (5.0 / R);
+    bdr = bm * sin_i; bdp = bm * cos_i;
+  } else if (R > 3.0) {
+    bdp = p[7];
+  }
+  bdr *= 1.0 - lfd; bdp *= 1.0 - lfd;
+  const double btor = exp(-fabs(z) / p[15]) * lfd *
+                      (z >= 0.0 ? p[10] * (1.0 - jf12_logistic(R, p[12], p[14]))
+                                : p[11] * (1.0 - jf12_logistic(R, p[13], p[14])));
+  const double xth = p[17] * 0.017453292519943295, tan_x = tan(xth);
+  const double rc_bound = p[18] + fabs(z) / tan_x;
+  const bool outer = R >= rc_bound;
+  const double rp = outer ? R - fabs(z) / tan_x : R * p[18] / rc_bound;
+  const double ratio = rp / R;
+  const double bxm = p[16] * exp(-rp / p[19]) * (outer ? ratio : ratio * ratio);
+  double thx = xth;
+  if (!outer) thx = (R - rp > 0.0) ? atan2(fabs(z), R - rp) : 1.5707963267948966;
+  const double bxr = bxm * cos(thx) * (z >= 0.0 ? 1.0 : -1.0), bxz = bxm * sin(thx);
+  const double br = bdr + bxr, bphi = bdp + btor;
+  b[0] = br * cp - bphi * sp;
+  b[1] = br * sp + bphi * cp;
+  b[2] = bxz;
+}
+
 __device__ __forceinline__ void lsa_pair(const DevGrid& g, const double* p, long long c0, bool has2,
                                          double* t) {
   double x, y, z;
@@ -117,6 +184,8 @@ __global__ void __launch_bounds__(256) field_b_kernel(const __grid_constant__ Fi
         for (int k = 0; k < 6; ++k) t[k] = a.p[f][k % 3];
       } else if (a.kind[f] == IMB_FIELD_LSA_B) {
         lsa_pair(a.g, a.p[f], 2 * q, (2 * q + 1) < a.g.ncell, t);
+      } else if (a.kind[f] == IMB_FIELD_JF12_B) {
+        model_pair(a.g, a.p[f], 2 * q, (2 * q + 1) < a.g.ncell, t, jf12_field);
       } else {  // IMB_FIELD_GAUSS_B: flat normal index n = 3*cell + comp, block n >> 1
         const unsigned long long seed = a.seeds[(size_t)a.seed_row[f] * a.n_real + r];
         const double mu = a.p[f][0], sigma = a.p[f][1];
@@ -168,6 +237,8 @@ __device__ __forceinline__ void generic_pair(const FieldArgs& a, unsigned int q,
       for (int k = 0; k < 6; ++k) t[k] = a.p[f][k % 3];
     } else if (a.kind[f] == IMB_FIELD_LSA_B) {
       lsa_pair(a.g, a.p[f], 2ll * q, (2ll * q + 1) < a.g.ncell, t);
+    } else if (a.kind[f] == IMB_FIELD_JF12_B) {
+      model_pair(a.g, a.p[f], 2ll * q, (2ll * q + 1) < a.g.ncell, t, jf12_field);
     } else {
       const unsigned long long seed = a.seeds[(size_t)a.seed_row[f] * a.n_real + r];
       const double mu = a.p[f][0], sigma = a.p[f][1];
@@ -192,7 +263,9 @@ __device__ __forceinline__ void generic_pair(const FieldArgs& a, unsigned int q,
 //                               corner component for the lane-per-realisation LOS kernel (los_rl.cu)
 // (Measured and dropped: an 8-wide layout storing (B(cell), B(cell + 1 in z)) pairs so that a z-pair
 // of corners is one 128-bit load -- 4.95 vs 5.03 ms, twice the memory.)
-template <int RL>
+// SIMPLE: the list is constants + ONE Gaussian field (the usual case): its own instantiation, so that the
+// register budget of the hot kernel is not set by the analytic models of the generic path
+template <int RL, bool SIMPLE>
 __global__ void __launch_bounds__(256) field_b_il_kernel(const __grid_constant__ FieldArgs a,
                                                          double* __restrict__ out) {
   __shared__ double2 s_tab[kTabSize];
@@ -201,14 +274,14 @@ __global__ void __launch_bounds__(256) field_b_il_kernel(const __grid_constant__
   const int g = blockIdx.y;
   const int rl = (int)(threadIdx.x % RL), r = g * RL + rl;
   const bool live = r < a.rows;
-  const bool simple = a.simple != 0;
+  constexpr bool simple = SIMPLE;
   const unsigned long long seed =
       (simple && live) ? a.seeds[(size_t)a.seed_row[a.gauss] * a.n_real + r] : 0ull;
   for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < npair_rl; w += gridDim.x * blockDim.x) {
     const unsigned int q = w / RL;
     double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (live) {
-      if (simple) simple_pair(a, seed, q, s_tab, v);
+      if (SIMPLE) simple_pair(a, seed, q, s_tab, v);
       else generic_pair(a, q, r, s_tab, v);
     }
     const long long c0 = 2ll * q;
@@ -412,7 +485,7 @@ int make_dev_grid(const imb_grid* grid, DevGrid* g) {
 
 static int field_type(int kind) {
   switch (kind) {
-    case IMB_FIELD_CONST_B: case IMB_FIELD_GAUSS_B: case IMB_FIELD_LSA_B: return 0;
+    case IMB_FIELD_CONST_B: case IMB_FIELD_GAUSS_B: case IMB_FIELD_LSA_B: case IMB_FIELD_JF12_B: return 0;
     case IMB_FIELD_CONST_NE: case IMB_FIELD_EXP_NE: case IMB_FIELD_COS_NE:
     case IMB_FIELD_RANDOM_NE: return 1;
     case IMB_FIELD_CRE_ANALYTIC: case IMB_FIELD_CRE_CONST: return 2;
@@ -528,7 +601,7 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
       a.kind[a.nfields] = fields[f].kind;
       a.stream[a.nfields] = (unsigned int)fields[f].stream;
       a.seed_row[a.nfields] = fields[f].seed_row;
-      for (int k = 0; k < 8; ++k) a.p[a.nfields][k] = fields[f].p[k];
+      for (int k = 0; k < 24; ++k) a.p[a.nfields][k] = fields[f].p[k];
       a.nfields++;
     }
     a.simple = a.has_const = a.gauss = 0;
@@ -560,9 +633,15 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
         int bx = grid_blocks(((g.ncell + 1) / 2) * rl, 256, 8) / n_groups;
         if (bx < 1) bx = 1;
         const dim3 grid(bx, n_groups);
-        if (rl == 32) field_b_il_kernel<32><<<grid, 256, 0, stream>>>(a, outs[type]);
-        else if (rl == 16) field_b_il_kernel<16><<<grid, 256, 0, stream>>>(a, outs[type]);
-        else field_b_il_kernel<8><<<grid, 256, 0, stream>>>(a, outs[type]);
+        if (a.simple) {
+          if (rl == 32) field_b_il_kernel<32, true><<<grid, 256, 0, stream>>>(a, outs[type]);
+          else if (rl == 16) field_b_il_kernel<16, true><<<grid, 256, 0, stream>>>(a, outs[type]);
+          else field_b_il_kernel<8, true><<<grid, 256, 0, stream>>>(a, outs[type]);
+        } else {
+          if (rl == 32) field_b_il_kernel<32, false><<<grid, 256, 0, stream>>>(a, outs[type]);
+          else if (rl == 16) field_b_il_kernel<16, false><<<grid, 256, 0, stream>>>(a, outs[type]);
+          else field_b_il_kernel<8, false><<<grid, 256, 0, stream>>>(a, outs[type]);
+        }
       } else if (b_stride == 3) {
         const bool vec = (addr % 16 == 0) && (need == 1 || row_elems % 2 == 0);
         if (vec) field_b_kernel<3, true><<<blocks, 256, 0, stream>>>(a, outs[type]);

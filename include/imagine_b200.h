@@ -59,8 +59,11 @@ enum {
   IMB_FIELD_RANDOM_NE = 5,    /* p = mean,std,min_ne, stochastic basic_fields.py:111-127  */
   IMB_FIELD_CRE_ANALYTIC = 6, /* p = j0,r0,z0,r_sun   (new: base_fields.py:104-113 stub;  */
   IMB_FIELD_CRE_CONST = 7,    /* p = j0                parameter names hamx/cre_analytic) */
-  IMB_FIELD_LSA_B = 8         /* p = b0 [uG], psi0, psi1, chi0 [rad], r0, z0, r_min, r_max [kpc]:  */
+  IMB_FIELD_LSA_B = 8,        /* p = b0 [uG], psi0, psi1, chi0 [rad], r0, z0, r_min, r_max [kpc]:  */
                               /* WMAP-3yr logarithmic spiral (parameter names hamx/breg_lsa.py:20-31) */
+  IMB_FIELD_JF12_B = 9        /* p = b_arm1..7, b_ring [uG], h_disk, w_disk [kpc], Bn, Bs [uG], rn, rs, */
+                              /* wh, z0 [kpc], B0_X [uG], Xtheta [deg], rpc_X, r0_X [kpc]: Jansson &    */
+                              /* Farrar 2012 regular field (names and order of hamx/breg_jf12.py:17-39) */
 };
 #define IMB_MAX_FIELDS 16
 
@@ -69,7 +72,7 @@ typedef struct {
   int32_t stream;   /* Philox stream id: decorrelates stochastic fields sharing a seed    */
   int32_t seed_row; /* row of the `seeds` table this field draws from (each FieldFactory  */
   int32_t reserved; /* owns its own seed list, pipelines/pipeline.py:805-813)             */
-  double p[8];      /* parameters in canonical units                                      */
+  double p[24];     /* parameters in canonical units (JF12 takes 20)                        */
 } imb_field_desc;
 
 /* ---- line-of-sight integration ----------------------------------------------------- */
@@ -92,6 +95,13 @@ typedef struct {
   int32_t n_peers;
   int32_t reserved;
   int64_t peer_delta[16];
+  /* Optional geometry cache (realisation-interleaved layouts only): a device buffer of             */
+  /* imb_los_geometry_bytes(m, n_steps) bytes filled by imb_los_geometry_build with THE SAME grid,   */
+  /* observer, dr, n_steps and directions.  The per-sample geometry of the ray march (trilinear      */
+  /* weights, cell, vertex-load mask) depends on those only -- not on the fields -- so a sampler     */
+  /* that evaluates thousands of parameter points builds it once.  NULL: computed on the fly.        */
+  const void* geometry;
+  int64_t geometry_bytes;
 } imb_los_cfg;
 
 /* ---- likelihood options ------------------------------------------------------------ */
@@ -176,6 +186,15 @@ int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg,
                       const double* cre, int rows_cre, int n_real,
                       double* out_dm, double* out_fd,
                       double* out_I, double* out_Q, double* out_U, void* stream);
+
+/*
+ * Geometry cache of the ray march (see imb_los_cfg.geometry): 80 bytes per (pixel, radial step).
+ * imb_los_geometry_build fills `cache` for `m` directions; asynchronous on `stream`.
+ */
+int64_t imb_los_geometry_bytes(int m, int n_steps);
+int imb_los_geometry_build(const imb_grid* grid, const imb_los_cfg* cfg, const double* dirs, int m,
+                           void* cache, int64_t cache_bytes, void* stream);
+
 
 /* PI = sqrt(Q^2+U^2), PA = atan2(U,Q)/2 (keys 'PI','PA', observable_dict.py:15-20) */
 int imb_pol_derive(const double* Q, const double* U, int64_t count,

@@ -24,13 +24,14 @@ used for the CPU baseline timing and the distribution checks.
 import numpy as np
 
 # field kinds -- must match include/imagine_b200.h (IMB_FIELD_*)
-CONST_B, GAUSS_B, CONST_NE, EXP_NE, COS_NE, RANDOM_NE, CRE_ANALYTIC, CRE_CONST, LSA_B = range(9)
+CONST_B, GAUSS_B, CONST_NE, EXP_NE, COS_NE, RANDOM_NE, CRE_ANALYTIC, CRE_CONST, LSA_B, JF12_B = range(10)
 
 TYPE_OF_KIND = {CONST_B: 'magnetic_field', GAUSS_B: 'magnetic_field',
                 CONST_NE: 'thermal_electron_density', EXP_NE: 'thermal_electron_density',
                 COS_NE: 'thermal_electron_density', RANDOM_NE: 'thermal_electron_density',
                 CRE_ANALYTIC: 'cosmic_ray_electron_density',
-                CRE_CONST: 'cosmic_ray_electron_density', LSA_B: 'magnetic_field'}
+                CRE_CONST: 'cosmic_ray_electron_density', LSA_B: 'magnetic_field',
+                JF12_B: 'magnetic_field'}
 STOCHASTIC_KINDS = (GAUSS_B, RANDOM_NE)
 
 
@@ -120,6 +121,77 @@ def lsa_B(grid, b0, psi0, psi1, chi0, r0=8.0, z0=1.0, r_min=3.0, r_max=20.0):
     cc = np.cos(chi)
     br, bphi = b0 * np.sin(psi) * cc, b0 * np.cos(psi) * cc
     out = np.stack([br * cp - bphi * sp, br * sp + bphi * cp, b0 * np.sin(chi)], axis=-1)
+    return np.where(ok[..., None], out, 0.0)
+
+
+# spiral-arm boundaries on the negative x axis [kpc] and relative cross-sections of the eight arm
+# regions (Jansson & Farrar 2012, ApJ 757, 14, section 5.1.1 / table 1)
+JF12_RC = (5.1, 6.3, 7.1, 8.3, 9.8, 11.4, 12.7, 15.5)
+JF12_F = (0.130, 0.165, 0.094, 0.122, 0.13, 0.118, 0.084, 0.156)
+JF12_PITCH_DEG = 11.5
+
+
+def jf12_B(grid, b_arm1, b_arm2, b_arm3, b_arm4, b_arm5, b_arm6, b_arm7, b_ring, h_disk, w_disk,
+           Bn, Bs, rn, rs, wh, z0, B0_X, Xtheta_deg, rpc_X, r0_X):
+    """
+    Jansson & Farrar (2012) regular Galactic magnetic field, the model behind hammurabiX's `breg_jf12`;
+    the reference only forwards the 20 parameters to the binary (fields/hamx/breg_jf12.py:17-39), so like
+    LSA it is defined here from the paper (eqs. 5-9), unpinned by reference code.  Parameter names and
+    order are the reference's.  Zero for r_spherical < 1 kpc and R > 20 kpc.
+      disk (R 3-5 kpc): azimuthal ring b_ring; (R > 5): eight logarithmic spiral regions of pitch 11.5 deg,
+        field b_i (5 kpc / R) along the spiral, b_8 fixed by flux conservation; x (1 - L(z, h_disk, w_disk))
+      toroidal halo: exp(-|z|/z0) L(z, h_disk, w_disk) Bn (1 - L(R, rn, wh))  (north; Bs, rs south)
+      X field: poloidal, elevation Xtheta outside r_p = rpc_X, b_X(r_p) = B0_X exp(-r_p / r0_X)
+    with L(x, h, w) = 1 / (1 + exp(-2 (|x| - h) / w)).
+    """
+    x, y, z = (v * np.ones(grid.shape) for v in grid.xyz())
+    R = np.sqrt(x**2 + y**2)
+    rsph = np.sqrt(R**2 + z**2)
+    Rs = np.where(R > 0, R, 1.0)
+    cp, sp = x / Rs, y / Rs
+    phi = np.arctan2(y, x)
+
+    def L(v, h, w):
+        return 1.0 / (1.0 + np.exp(-2.0 * (np.abs(v) - h) / w))
+
+    pitch = np.deg2rad(JF12_PITCH_DEG)
+    sin_i, cos_i = np.sin(pitch), np.cos(pitch)
+    b = [b_arm1, b_arm2, b_arm3, b_arm4, b_arm5, b_arm6, b_arm7]
+    b8 = -sum(f * bi for f, bi in zip(JF12_F[:7], b)) / JF12_F[7]
+    b.append(b8)
+    # disk
+    lfd = L(z, h_disk, w_disk)
+    # radius at which the spiral through (R, phi) crosses the negative x axis, folded into [rc_8/e^(2pi tan), rc_8]
+    r_negx = R * np.exp(-(phi - np.pi) / np.tan(np.pi / 2.0 - pitch))
+    for _ in range(2):
+        r_negx = np.where(r_negx > JF12_RC[7], R * np.exp(-(phi + np.pi) / np.tan(np.pi / 2.0 - pitch)), r_negx)
+        r_negx = np.where(r_negx > JF12_RC[7], R * np.exp(-(phi + 3.0 * np.pi) / np.tan(np.pi / 2.0 - pitch)), r_negx)
+    arm = np.zeros(grid.shape)
+    for i in range(7, -1, -1):
+        arm = np.where(r_negx < JF12_RC[i], b[i], arm)
+    bmag_spiral = arm * (5.0 / Rs)
+    b_disk_r = np.where(R > 5.0, bmag_spiral * sin_i, 0.0)
+    b_disk_phi = np.where(R > 5.0, bmag_spiral * cos_i, np.where(R > 3.0, b_ring, 0.0))
+    b_disk_r, b_disk_phi = b_disk_r * (1.0 - lfd), b_disk_phi * (1.0 - lfd)
+    # toroidal halo
+    b_tor = np.exp(-np.abs(z) / z0) * lfd * np.where(z >= 0, Bn * (1.0 - L(R, rn, wh)), Bs * (1.0 - L(R, rs, wh)))
+    # X field
+    tan_x = np.tan(np.deg2rad(Xtheta_deg))
+    rc_bound = rpc_X + np.abs(z) / tan_x
+    outer = R >= rc_bound
+    rp_out = R - np.abs(z) / tan_x
+    rp_in = R * rpc_X / rc_bound
+    rp = np.where(outer, rp_out, rp_in)
+    bx_mag = B0_X * np.exp(-rp / r0_X) * np.where(outer, rp / Rs, (rp / Rs) ** 2)
+    theta_x = np.where(outer, np.deg2rad(Xtheta_deg),
+                       np.arctan2(np.abs(z), np.where(outer, 1.0, R - rp_in)))
+    theta_x = np.where((~outer) & (R - rp_in <= 0), np.pi / 2.0, theta_x)
+    b_x_r = bx_mag * np.cos(theta_x) * np.where(z >= 0, 1.0, -1.0)
+    b_x_z = bx_mag * np.sin(theta_x)
+    br = b_disk_r + b_x_r
+    bphi = b_disk_phi + b_tor
+    out = np.stack([br * cp - bphi * sp, br * sp + bphi * cp, b_x_z], axis=-1)
+    ok = (rsph >= 1.0) & (R <= 20.0) & (R > 0)
     return np.where(ok[..., None], out, 0.0)
 
 
@@ -252,6 +324,8 @@ def evaluate_fields(grid, descs, seeds, rng='philox'):
                     f = constant_B(grid, *p[:3])
                 elif kind == LSA_B:
                     f = lsa_B(grid, *p[:8])
+                elif kind == JF12_B:
+                    f = jf12_B(grid, *p[:20])
                 elif kind == GAUSS_B:
                     f = (gaussian_B_philox(grid, p[0], p[1], seeds[r], stream) if rng == 'philox'
                          else gaussian_B_reference(grid, p[0], p[1], seeds[r]))

@@ -52,8 +52,8 @@ def test_compute_entry_points_refuse_without_init(lib):
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_lib.Grid) == 64
-    assert C.sizeof(_lib.FieldDesc) == 80
-    assert C.sizeof(_lib.LosCfg) == 232
+    assert C.sizeof(_lib.FieldDesc) == 208
+    assert C.sizeof(_lib.LosCfg) == 248
 
 
 def test_field_layout_selection_host_only(lib):

@@ -438,3 +438,29 @@ def test_reference_test_simulator_equals_the_gpu_test_simulator(api):
     got = api.B200TestSimulator(M)(fields)[key].data
     assert got.shape == want.shape == (2, 7)
     assert np.allclose(got, want, rtol=1e-12, atol=0)
+
+
+def test_masks_inside_the_simulator(api):
+    """hammurabi.py:281-325: one identical mask for every observable, applied while simulating -- masked
+    pixels are not marched (zeros), kept pixels are bit-identical to the unmasked run."""
+    nside, N = 4, 4
+    grid, meas, keys, fields, _ = _los_setup(api, nside, N)
+    m = 12 * nside ** 2
+    keep = (np.arange(m) % 5 != 0).astype(float).reshape(1, -1)
+    masks = api.Masks()
+    for k in keys:
+        masks.append(name=k, data=keep, otype='HEALPix')
+    full = api.B200Simulator(meas, radial_step=0.2)(fields)
+    masked = api.B200Simulator(meas, radial_step=0.2, masks=masks)(fields)
+    b = keep[0].astype(bool)
+    for k in keys:
+        assert masked[k].shape == (N, m)
+        assert np.array_equal(masked[k].data[:, b], full[k].data[:, b]), k
+        assert (masked[k].data[:, ~b] == 0).all(), k
+    # the masked likelihood sees the same numbers either way
+    lk = api.B200EnsembleLikelihood(meas, mask_dict=masks)
+    assert lk(masked) == lk(full)
+    partial = api.Masks()
+    partial.append(name=keys[0], data=keep, otype='HEALPix')
+    with pytest.raises(AssertionError):
+        api.B200Simulator(meas, masks=partial)

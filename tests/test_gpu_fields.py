@@ -164,3 +164,24 @@ def test_lsa_field_matches_oracle(eng, bs):
     mid = np.abs(z[inside]) < 1e-9
     psi = np.radians(27.0) + np.radians(0.9) * np.log(R[inside][mid] / 8.0)
     assert np.allclose(br[mid], 6.0 * np.sin(psi), rtol=1e-10)
+
+
+def test_jf12_regular_field_matches_oracle(eng):
+    """Jansson & Farrar 2012 (hamx/breg_jf12.py parameter set): CUDA vs oracle/fields.py:jf12_B, 1e-9."""
+    p = [0.1, 3.0, -0.9, -0.8, -2.0, -4.2, 0.0, 0.1, 0.40, 0.27, 1.4, -1.1, 9.22, 16.7, 0.20, 5.3, 4.6, 49, 4.8, 2.9]
+    for res in ([33, 31, 9], [41, 41, 17]):
+        grid = eng.DeviceGrid(BOX, res)
+        og = OF.Grid(BOX, res)
+        got = eng.field_eval(grid, [(OF.JF12_B, p, 0)], [0], b_stride=3)['magnetic_field']
+        got = got.cpu().numpy().reshape(*og.shape, 3)
+        want = OF.jf12_B(og, *p)
+        assert np.abs(want).max() > 1.0
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-12)
+    # summed with a Gaussian component in the wide layout (generic path of the interleaved kernel)
+    grid, og = eng.DeviceGrid(BOX, [20, 18, 12]), OF.Grid(BOX, [20, 18, 12])
+    descs = [(OF.JF12_B, p, 0), (OF.GAUSS_B, [0.0, 1.5], 1)]
+    f = eng.field_eval(grid, descs, [11, 12, 13], b_stride=24)['magnetic_field']
+    from tests.helpers import b_to_reference_layout
+    got = b_to_reference_layout(f, 3, og.shape)
+    want = OF.evaluate_fields(og, descs, [11, 12, 13])['magnetic_field']
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-11)
