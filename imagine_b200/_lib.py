@@ -47,8 +47,7 @@ class LosCfg(C.Structure):
                 ('out_cols_per_dest', C.c_int32), ('nu_ghz', C.c_double), ('alpha', C.c_double),
                 ('beta', C.c_double), ('theta', C.c_double), ('e0_gev', C.c_double),
                 ('sync_k', C.c_double), ('out_dest_stride', C.c_int64), ('n_peers', C.c_int32),
-                ('reserved', C.c_int32), ('peer_delta', C.c_int64 * 16),
-                ('geometry', C.c_void_p), ('geometry_bytes', C.c_int64)]
+                ('reserved', C.c_int32), ('peer_delta', C.c_int64 * 16)]
 
 
 _P = C.c_void_p
@@ -68,8 +67,6 @@ _SIGNATURES = {
     'imb_los_integrate': (C.c_int, [C.POINTER(Grid), C.POINTER(LosCfg), _P, C.c_int, _P, C.c_int,
                                     C.c_int, _P, C.c_int, _P, C.c_int, C.c_int,
                                     _P, _P, _P, _P, _P, _P]),
-    'imb_los_geometry_bytes': (C.c_int64, [C.c_int, C.c_int]),
-    'imb_los_geometry_build': (C.c_int, [C.POINTER(Grid), C.POINTER(LosCfg), _P, C.c_int, _P, C.c_int64, _P]),
     'imb_pol_derive': (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     'imb_ensemble_mean': (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     'imb_ensemble_var': (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),

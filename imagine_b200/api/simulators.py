@@ -193,7 +193,6 @@ class B200Simulator(Simulator):
         self._evaluator = None
         self.rank, self.world, self.group = int(rank), int(world), group
         self._dirs = {}
-        self._geo = {}
         self._row_cache = (None, {})
         for key in self.observables:
             name, freq, nside, tag = key
@@ -259,15 +258,6 @@ class B200Simulator(Simulator):
             self._dirs[nside] = engine.healpix_ring_dirs(int(nside))
         return self._dirs[nside]
 
-    def _geometry_for(self, dg, nside, settings, dirs):
-        """Geometry cache of the ray march per Nside (engine.LosGeometry); rebuilt when the grid, the
-        sampling or the (masked) direction set changes."""
-        geo = self._geo.get(nside)
-        if geo is None or not geo.matches(dg, settings, dirs):
-            geo = engine.LosGeometry(dg, settings, dirs)
-            self._geo[nside] = geo
-        return geo
-
     # -- the integrator for a block of realisations --------------------------------------------------
     def _integrate(self, dg, fields, n_real, sharded=None):
         """
@@ -313,17 +303,16 @@ class B200Simulator(Simulator):
                 if freq is not None:
                     kw['nu_ghz'] = freq
                 settings = engine.LosSettings(**kw)
-                geo = self._geometry_for(dg, nside, settings, dirs) if B.dim() == 4 else None
                 if sharded is not None:
                     views, layout = sharded
                     out = {(k[0] if k[0] in ('fd', 'dm') else k[3]): views[k] for k in keys}
                     engine.los_integrate(dg, settings, dirs, B, ne,
                                          cre if want & {'I', 'Q', 'U'} else None, n_real=n_real,
-                                         want=tuple(want), out=out, out_layout=layout, geometry=geo)
+                                         want=tuple(want), out=out, out_layout=layout)
                     continue
                 maps = engine.los_integrate(dg, settings, dirs, B, ne,
                                             cre if want & {'I', 'Q', 'U'} else None,
-                                            n_real=n_real, want=tuple(want), geometry=geo)
+                                            n_real=n_real, want=tuple(want))
                 derived = None
                 for k in keys:
                     if k[0] in ('fd', 'dm'):
@@ -449,7 +438,6 @@ class B200Simulator(Simulator):
     def __getstate__(self):
         state = dict(self.__dict__)
         state['_dirs'] = {}
-        state['_geo'] = {}
         state['_kept'] = {}
         state['_evaluator'] = None
         state['_send'] = None

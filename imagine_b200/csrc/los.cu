@@ -16,7 +16,6 @@ namespace imb {
 
 int make_dev_grid(const imb_grid* grid, DevGrid* g);
 int launch_los_rl(const LosArgs& a, int rl, bool has_ne, bool has_cre, bool var_p, cudaStream_t s);
-int launch_los_geometry(const LosArgs& a, void* cache, cudaStream_t s);
 
 template <bool HAS_NE, bool HAS_CRE, bool VAR_P, int RT, int BS>
 __global__ void __launch_bounds__(256) los_kernel(const __grid_constant__ LosArgs a) {
@@ -264,13 +263,6 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
     a.out_dest = cfg->out_dest_stride;
   }
   a.n_peers = 0;
-  a.geometry = nullptr;
-  if (cfg->geometry) {
-    if (cfg->geometry_bytes < imb_los_geometry_bytes(m, cfg->n_steps) ||
-        reinterpret_cast<uintptr_t>(cfg->geometry) % 16 != 0)
-      return IMB_EINVAL;
-    a.geometry = cfg->geometry;
-  }
   if (cfg->n_peers > 0) {
     if (cfg->n_peers > 16 || cfg->out_cols_per_dest <= 0 || m / cfg->out_cols_per_dest != cfg->n_peers)
       return IMB_EINVAL;
@@ -323,30 +315,3 @@ extern "C" int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg, c
   }
   return IMB_OK;
 }
-
-extern "C" int64_t imb_los_geometry_bytes(int m, int n_steps) {
-  if (m < 0 || n_steps < 0) return 0;
-  return (int64_t)80 * (int64_t)m * (int64_t)n_steps + 256;
-}
-
-extern "C" int imb_los_geometry_build(const imb_grid* grid, const imb_los_cfg* cfg, const double* dirs, int m,
-                                      void* cache, int64_t cache_bytes, void* stream) {
-  IMB_TRY(check_init());
-  LosArgs a;
-  IMB_TRY(make_dev_grid(grid, &a.g));
-  if (!cfg || !dirs || !cache || m < 0 || cfg->n_steps < 0 || !(cfg->dr > 0.0)) return IMB_EINVAL;
-  if (cache_bytes < imb_los_geometry_bytes(m, cfg->n_steps) || reinterpret_cast<uintptr_t>(cache) % 16 != 0)
-    return IMB_EINVAL;
-  for (int k = 0; k < 3; ++k)
-    if (grid->n[k] < 2 || !(grid->hi[k] > grid->lo[k])) return IMB_EINVAL;
-  if (m == 0 || cfg->n_steps == 0) return IMB_OK;
-  for (int k = 0; k < 3; ++k) a.obs[k] = cfg->observer[k];
-  a.dr = cfg->dr;
-  a.n_steps = cfg->n_steps;
-  a.m = m;
-  a.dirs = dirs;
-  IMB_TRY(launch_los_geometry(a, cache, (cudaStream_t)stream));
-  IMB_LAUNCHED();
-  return IMB_OK;
-}
-

@@ -27,7 +27,6 @@ struct LosArgs {
   // NVLink; peer_delta[d] = (peer d's buffer base) - (my buffer base), in doubles
   int n_peers;
   long long peer_delta[16];
-  const void* geometry;    // optional geometry cache of the realisation-lane kernel (los_rl.cu), else NULL
 };
 
 __device__ __forceinline__ long long out_index(const LosArgs& a, int rr, int pix) {

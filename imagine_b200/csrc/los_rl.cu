@@ -38,7 +38,10 @@
 // take adjacent pixels from a per-SM work list (to turn the neighbouring rays' shared vertex lines into L1
 // hits: L1 hit rate is 13 % with one-pixel blocks placed by the hardware scheduler): 2.18 vs 2.05 ms at
 // C3, 5.79 vs 5.67 ms on a C4 shard -- the atomics, the extra barrier and 60 bytes of spills cost more
-// than the L2 round trips they save.
+// than the L2 round trips they save.  A geometry cache (weights, cell and load mask of every (pixel, step)
+// built once per grid / observer / direction set, 80 B per sample, read back by phase A instead of being
+// recomputed): bit-identical maps, but 2.23 vs 2.16 ms at 64 realisations, 1.10 vs 1.14 at 32, 0.56 vs 0.55
+// at 8 -- phase A is bound by its block-wide barrier and the (n_e, CRE) gathers, not by the arithmetic.
 // Numeric definition: oracle/los.py.
 #include <cstdlib>
 #include <type_traits>
@@ -67,15 +70,6 @@ struct __align__(16) RlGeo {   // per (segment, step slot): everything realisati
   double dm;                   // n_e dl of the step (shared-n_e dispersion measure); bit 11 of code: inside the box
   int pad[4];                  // 112 bytes: conflict-free 128-bit stores
 };
-
-// geometry cache entry of (pixel, radial step j): what phase A derives from the grid and the ray alone
-// (imb_los_geometry_build); code as RlGeo.code, computed against step j - 1
-struct __align__(16) RlCache {
-  double w[8];
-  int base, code;
-  int pad[2];
-};
-static_assert(sizeof(RlCache) == 80, "imb_los_geometry_bytes assumes 80-byte entries");
 
 // three predicated 64-bit loads (the x, y, z components of one vertex slot) in program order
 template <int RL>
@@ -145,104 +139,10 @@ __device__ __forceinline__ RlCell rl_cell(const LosArgs& a, const RlPix& pc, int
   return c;
 }
 
-// per-pixel prologue: sky basis and the conservative in-box step range (the exact in-box test is still
-// done per step); lane k < 3 of the calling warp intersects the ray with the slab of axis k
-__device__ __forceinline__ void rl_pixel_setup(const LosArgs& a, double inv_dr, int pix, int lane, RlPix& pc) {
-  const double nx = a.dirs[3 * pix], ny = a.dirs[3 * pix + 1], nz = a.dirs[3 * pix + 2];
-  double tmin = 0.0, tmax = a.dr * (double)a.n_steps;
-  if (lane < 3) {
-    const double nk = lane == 0 ? nx : (lane == 1 ? ny : nz);
-    const double lo = a.g.lo[lane], hi = lo + (double)(a.g.n[lane] - 1) / a.g.inv_step[lane];
-    if (nk != 0.0) {
-      const double t1 = (lo - a.obs[lane]) / nk, t2 = (hi - a.obs[lane]) / nk;
-      tmin = fmax(tmin, fmin(t1, t2));
-      tmax = fmin(tmax, fmax(t1, t2));
-    } else if (a.obs[lane] < lo || a.obs[lane] > hi) {
-      tmax = -1.0;
-    }
-  }
-#pragma unroll
-  for (int o = 1; o < 4; o <<= 1) {
-    tmin = fmax(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
-    tmax = fmin(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-  }
-  if (lane == 0) {
-    const double sth = sqrt(nx * nx + ny * ny);
-    pc.n[0] = nx; pc.n[1] = ny; pc.n[2] = nz;
-    pc.st = sth; pc.ct = nz;
-    pc.cp = sth > 0.0 ? nx / sth : 1.0;
-    pc.sp = sth > 0.0 ? ny / sth : 0.0;
-    int j_lo = 0, j_hi = -1;
-    if (tmax >= tmin) {
-      j_lo = max(0, (int)floor(tmin * inv_dr - 0.5) - 1);
-      j_hi = min(a.n_steps - 1, (int)ceil(tmax * inv_dr - 0.5) + 1);
-    }
-    pc.j_lo = j_lo; pc.j_hi = j_hi;
-  }
-}
-
-// geometry of step j: trilinear weights in slot order, the all-even vertex, the load mask against the cell
-// of step j - 1 (`has_prev`: j - 1 belongs to the same marched segment).  Returns false outside the box.
-__device__ __forceinline__ bool rl_step_geometry(const LosArgs& a, const RlPix& pc, int sx, int sy, int j,
-                                                 bool valid, bool has_prev, double* w, int& base, int& code,
-                                                 RlCell& c) {
-  c = rl_cell(a, pc, j, valid);
-  code = 0;
-  base = 0;
-  if (!c.inside) {
-#pragma unroll
-    for (int s = 0; s < 8; ++s) w[s] = 0.0;
-    return false;
-  }
-  const int ix = c.ix, iy = c.iy, iz = c.iz;
-  const double tx = c.ux - (double)ix, ty = c.uy - (double)iy, tz = c.uz - (double)iz;
-  const int qx = ix & 1, qy = iy & 1, qz = iz & 1;
-  int cx = 3, cy = 3, cz = 3;                        // bit s: the vertex of parity s changed
-  const RlCell pr = rl_cell(a, pc, j - 1, has_prev);
-  if (pr.inside) {
-    cx = (ix + qx != pr.ix + (pr.ix & 1) ? 1 : 0) | (ix + 1 - qx != pr.ix + 1 - (pr.ix & 1) ? 2 : 0);
-    cy = (iy + qy != pr.iy + (pr.iy & 1) ? 1 : 0) | (iy + 1 - qy != pr.iy + 1 - (pr.iy & 1) ? 2 : 0);
-    cz = (iz + qz != pr.iz + (pr.iz & 1) ? 1 : 0) | (iz + 1 - qz != pr.iz + 1 - (pr.iz & 1) ? 2 : 0);
-  }
-#pragma unroll
-  for (int s = 0; s < 8; ++s)
-    if (((cx >> (s >> 2)) | (cy >> ((s >> 1) & 1)) | (cz >> (s & 1))) & 1) code |= 1 << s;
-  code |= (qx << 8) | (qy << 9) | (qz << 10) | (1 << 11);
-  // the slot of parity s along an axis holds the vertex i (weight 1 - t) when s == i & 1, else i + 1 (t)
-  const double wx[2] = {qx ? tx : 1.0 - tx, qx ? 1.0 - tx : tx};
-  const double wy[2] = {qy ? ty : 1.0 - ty, qy ? 1.0 - ty : ty};
-  const double wz[2] = {qz ? tz : 1.0 - tz, qz ? 1.0 - tz : tz};
-#pragma unroll
-  for (int s = 0; s < 8; ++s) w[s] = wx[s >> 2] * wy[(s >> 1) & 1] * wz[s & 1];
-  base = (ix * a.g.n[1] + iy) * a.g.n[2] + iz + qx * sx + qy * sy + qz;
-  return true;
-}
-
-// imb_los_geometry_build: one warp per pixel, lanes over the steps of the conservative in-box range
-__global__ void __launch_bounds__(256) los_rl_geometry_kernel(const __grid_constant__ LosArgs a, double inv_dr,
-                                                              int sx, int sy, RlCache* __restrict__ cache) {
-  __shared__ RlPix s_pix[8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int pix = blockIdx.x * 8 + warp;
-  if (pix >= a.m) return;
-  RlPix& pc = s_pix[warp];
-  rl_pixel_setup(a, inv_dr, pix, lane, pc);
-  __syncwarp();
-  const int j_lo = pc.j_lo, j_hi = pc.j_hi;
-  for (int j = j_lo + lane; j <= j_hi; j += 32) {
-    RlCache e;
-    RlCell c;
-    rl_step_geometry(a, pc, sx, sy, j, true, j > j_lo, e.w, e.base, e.code, c);
-    e.pad[0] = e.pad[1] = 0;
-    cache[(size_t)pix * a.n_steps + j] = e;
-  }
-}
-
 // SHARED: every scalar grid present (n_e, CRE) is one grid for all realisations -- the usual case;
 // the per-realisation gathers of RandomThermalElectrons are then compiled out of the march.
 // G: warps (realisation groups) per block.
-// CACHED: phase A reads weights / cell / load mask from the geometry cache (imb_los_cfg.geometry).
-template <int RL, bool HAS_NE, bool HAS_CRE, bool VAR_P, bool P3, bool SHARED, int G, bool CACHED>
+template <int RL, bool HAS_NE, bool HAS_CRE, bool VAR_P, bool P3, bool SHARED, int G>
 __global__ void __launch_bounds__(32 * G, IMB_LOS_WARPS_PER_SM / G)
 los_rl_kernel(const __grid_constant__ RlArgs ra) {
   const LosArgs& a = ra.a;
@@ -265,7 +165,41 @@ los_rl_kernel(const __grid_constant__ RlArgs ra) {
   const bool live = active && rr < a.n_real;
   RlPix& pc = s_pix;
 
-  if (warp == 0) rl_pixel_setup(a, ra.inv_dr, pix, lane, pc);
+  if (warp == 0) {
+    const double nx = a.dirs[3 * pix], ny = a.dirs[3 * pix + 1], nz = a.dirs[3 * pix + 2];
+    // conservative in-box step range (the exact in-box test is still done per step): lane k < 3
+    // intersects the ray with the slab of axis k
+    double tmin = 0.0, tmax = a.dr * (double)a.n_steps;
+    if (lane < 3) {
+      const double nk = lane == 0 ? nx : (lane == 1 ? ny : nz);
+      const double lo = a.g.lo[lane], hi = lo + (double)(a.g.n[lane] - 1) / a.g.inv_step[lane];
+      if (nk != 0.0) {
+        const double t1 = (lo - a.obs[lane]) / nk, t2 = (hi - a.obs[lane]) / nk;
+        tmin = fmax(tmin, fmin(t1, t2));
+        tmax = fmin(tmax, fmax(t1, t2));
+      } else if (a.obs[lane] < lo || a.obs[lane] > hi) {
+        tmax = -1.0;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+      tmin = fmax(tmin, __shfl_xor_sync(FULL, tmin, o));
+      tmax = fmin(tmax, __shfl_xor_sync(FULL, tmax, o));
+    }
+    if (lane == 0) {
+      const double sth = sqrt(nx * nx + ny * ny);
+      pc.n[0] = nx; pc.n[1] = ny; pc.n[2] = nz;
+      pc.st = sth; pc.ct = nz;
+      pc.cp = sth > 0.0 ? nx / sth : 1.0;
+      pc.sp = sth > 0.0 ? ny / sth : 0.0;
+      int j_lo = 0, j_hi = -1;
+      if (tmax >= tmin) {
+        j_lo = max(0, (int)floor(tmin * ra.inv_dr - 0.5) - 1);
+        j_hi = min(a.n_steps - 1, (int)ceil(tmax * ra.inv_dr - 0.5) + 1);
+      }
+      pc.j_lo = j_lo; pc.j_hi = j_hi;
+    }
+  }
   s_dm[warp][lane] = 0.0;
   __syncthreads();
 
@@ -292,43 +226,20 @@ los_rl_kernel(const __grid_constant__ RlArgs ra) {
       const int off = cb + istep;
       const int j_hi = pc.j_hi;
       const int j = pc.j_lo + seg * seg_len + off;
-      const bool valid = off < seg_len && j <= j_hi;
-      RlGeo& ge = s_geo[seg * CH + istep];
-      double w[8];
-      int base, code;
-      RlCell c;
-      bool inside;
-      if (CACHED) {
-        // weights, cell and load mask from the cache; a segment's first step finds nothing resident
-        const RlCache* e = static_cast<const RlCache*>(a.geometry) + ((size_t)pix * a.n_steps + (valid ? j : 0));
-        const double2* e2 = reinterpret_cast<const double2*>(e);
-        double2 q[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) q[k] = valid ? __ldg(e2 + k) : make_double2(0.0, 0.0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { w[2 * k] = q[k].x; w[2 * k + 1] = q[k].y; }
-        base = __double2loint(q[4].x);
-        code = __double2hiint(q[4].x);
-        inside = (code >> 11) & 1;
-        if (S > 1 && inside && off == 0) code |= 0xff;
-      } else {
-        inside = rl_step_geometry(a, pc, sx, sy, j, valid, off > 0, w, base, code, c);
-      }
+      const RlCell c = rl_cell(a, pc, j, off < seg_len && j <= j_hi);
+      const int ix = c.ix, iy = c.iy, iz = c.iz;
+      const bool inside = c.inside;
+      Cell cc;
+      cc.base = ((long long)ix * a.g.n[1] + iy) * a.g.n[2] + iz;
+      cc.sy = sy; cc.sx = sx;
+      cc.tx = c.ux - (double)ix; cc.ty = c.uy - (double)iy; cc.tz = c.uz - (double)iz;
       double ne_s = 0.0, cre_s = 0.0;
       if (inside) {
-        // shared n_e / CRE at the sample: the same 8 vertices and weights as the field (slot order)
-        const int dx = (code & 0x100) ? -sx : sx, dy = (code & 0x200) ? -sy : sy, dz = (code & 0x400) ? -1 : 1;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          const int idx = base + ((s & 4) ? dx : 0) + ((s & 2) ? dy : 0) + ((s & 1) ? dz : 0);
-          if (HAS_NE && HAS_CRE && a.necre) {
-            const double2 pr2 = __ldg(reinterpret_cast<const double2*>(a.necre) + idx);
-            ne_s = fma(w[s], pr2.x, ne_s);
-            cre_s = fma(w[s], pr2.y, cre_s);
-          } else {
-            if (ne_shared) ne_s = fma(w[s], __ldg(a.ne + idx), ne_s);
-            if (cre_shared) cre_s = fma(w[s], __ldg(a.cre + idx), cre_s);
-          }
+        if (HAS_NE && HAS_CRE && a.necre) {
+          interp_pair(a.necre, cc, ne_s, cre_s);
+        } else {
+          if (ne_shared) ne_s = interp_scalar(a.ne, cc);
+          if (cre_shared) cre_s = interp_scalar(a.cre, cc);
         }
       }
       double kp = a.sync_k;
@@ -340,15 +251,36 @@ los_rl_kernel(const __grid_constant__ RlArgs ra) {
         s_var[seg * CH + istep][1] = (p + 1.0) / (p + 7.0 / 3.0);
         s_var[seg * CH + istep][2] = (p + 1.0) * 0.25;
       }
+      // which slots hold a different vertex than after the previous step of this segment (its cell is
+      // recomputed here: cheaper than passing it between lanes and warps)
+      const int qx = ix & 1, qy = iy & 1, qz = iz & 1;
+      int code = 0;
+      if (inside) {
+        int cx = 3, cy = 3, cz = 3;                        // bit s: the vertex of parity s changed
+        const RlCell pr = rl_cell(a, pc, j - 1, off > 0);
+        if (pr.inside) {
+          cx = (ix + qx != pr.ix + (pr.ix & 1) ? 1 : 0) | (ix + 1 - qx != pr.ix + 1 - (pr.ix & 1) ? 2 : 0);
+          cy = (iy + qy != pr.iy + (pr.iy & 1) ? 1 : 0) | (iy + 1 - qy != pr.iy + 1 - (pr.iy & 1) ? 2 : 0);
+          cz = (iz + qz != pr.iz + (pr.iz & 1) ? 1 : 0) | (iz + 1 - qz != pr.iz + 1 - (pr.iz & 1) ? 2 : 0);
+        }
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        reinterpret_cast<double2*>(ge.w)[k] = make_double2(w[2 * k], w[2 * k + 1]);
+        for (int s = 0; s < 8; ++s)
+          if (((cx >> (s >> 2)) | (cy >> ((s >> 1) & 1)) | (cz >> (s & 1))) & 1) code |= 1 << s;
+        code |= (qx << 8) | (qy << 9) | (qz << 10) | (1 << 11);
+      }
+      // the slot of parity s along an axis holds the vertex i (weight 1 - t) when s == i & 1, else i + 1 (t)
+      RlGeo& ge = s_geo[seg * CH + istep];
+      const double wx[2] = {qx ? cc.tx : 1.0 - cc.tx, qx ? 1.0 - cc.tx : cc.tx};
+      const double wy[2] = {qy ? cc.ty : 1.0 - cc.ty, qy ? 1.0 - cc.ty : cc.ty};
+      const double wz[2] = {qz ? cc.tz : 1.0 - cc.tz, qz ? 1.0 - cc.tz : cc.tz};
+#pragma unroll
+      for (int s = 0; s < 8; ++s) ge.w[s] = wx[s >> 2] * wy[(s >> 1) & 1] * wz[s & 1];
       const double dlf = a.dl_pc * ((HAS_NE && HAS_CRE) ? 2.0 * a.lam2 : 1.0);
       // the realisation-independent leading factors are folded in here:
       // -0.812 n_e dl [2 lambda^2] (Faraday; the sign of B_par = -B.n rides along) and CRE K(p) [dl]
       ge.ne = -(__dmul_rn(0.812, ne_s) * dlf);
       ge.cre = P3 ? cre_s * kp * a.dl_cm : cre_s * kp;
-      ge.base = base;
+      ge.base = (int)cc.base + qx * sx + qy * sy + qz;
       ge.code = code;
       ge.dm = ne_s * a.dl_pc;
       // in-box steps among those this warp prepared, any segment
@@ -596,19 +528,15 @@ static int launch_rl_variant(const LosArgs& a, cudaStream_t s) {
   ra.sx = a.g.n[1] * a.g.n[2];
   ra.n_groups = n_groups;
   const bool shared = (!HAS_NE || a.ne_row == 0) && (!HAS_CRE || a.cre_row == 0);
-  const bool cached = a.geometry != nullptr && shared && !VAR_P;
   if (RL == 32 && shared && n_groups >= 2) {
     // two realisation groups of a pixel share one geometry pass
     dim3 grid(a.m, (n_groups + 1) / 2);
-    constexpr int G2 = RL == 32 ? 2 : 1;
-    if (cached) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, G2, !VAR_P><<<grid, 32 * G2, 0, s>>>(ra);
-    else los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, G2, false><<<grid, 32 * G2, 0, s>>>(ra);
+    los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, (RL == 32 ? 2 : 1)><<<grid, 64, 0, s>>>(ra);
     return IMB_OK;
   }
   dim3 grid(a.m, n_groups);
-  if (cached) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, 1, !VAR_P><<<grid, 32, 0, s>>>(ra);
-  else if (shared) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, 1, false><<<grid, 32, 0, s>>>(ra);
-  else los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, false, 1, false><<<grid, 32, 0, s>>>(ra);
+  if (shared) los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, true, 1><<<grid, 32, 0, s>>>(ra);
+  else los_rl_kernel<RL, HAS_NE, HAS_CRE, VAR_P, P3, false, 1><<<grid, 32, 0, s>>>(ra);
   return IMB_OK;
 }
 
@@ -633,14 +561,6 @@ int launch_los_rl(const LosArgs& a, int rl, bool has_ne, bool has_cre, bool var_
   if (rl == 32) return launch_rl<32>(a, has_ne, has_cre, var_p, s);
   if (rl == 16) return launch_rl<16>(a, has_ne, has_cre, var_p, s);
   return launch_rl<8>(a, has_ne, has_cre, var_p, s);
-}
-
-// imb_los_geometry_build
-int launch_los_geometry(const LosArgs& a, void* cache, cudaStream_t s) {
-  if (a.g.ncell >= (1ll << 31)) return IMB_EUNSUPPORTED;
-  los_rl_geometry_kernel<<<(a.m + 7) / 8, 256, 0, s>>>(a, 1.0 / a.dr, a.g.n[1] * a.g.n[2], a.g.n[2],
-                                                       static_cast<RlCache*>(cache));
-  return IMB_OK;
 }
 
 }  // namespace imb

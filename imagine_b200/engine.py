@@ -186,35 +186,8 @@ def healpix_ring_dirs(nside):
     return out
 
 
-class LosGeometry:
-    """
-    Geometry cache of the ray march (imb_los_geometry_build): trilinear weights, cell and vertex-load
-    mask of every (pixel, radial step).  It depends on the grid, the observer, the radial sampling and
-    the directions only -- not on the fields -- so whoever evaluates many parameter points builds it
-    once.  The object remembers what it was built for; `los_integrate` refuses a mismatching one.
-    """
-
-    def __init__(self, grid, settings, dirs):
-        torch = _torch()
-        L.init()
-        self.dirs = _f64(dirs, 'dirs').reshape(-1, 3)
-        self.key = (tuple(map(float, grid.box.ravel())), tuple(map(int, grid.resolution)), settings.observer,
-                    settings.dr, settings.n_steps)
-        m = self.dirs.shape[0]
-        nbytes = int(L.load().imb_los_geometry_bytes(m, settings.n_steps))
-        self.buffer = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=self.dirs.device)
-        cfg = settings.c_struct()
-        L.check(L.load().imb_los_geometry_build(C.byref(grid.c), C.byref(cfg), L.ptr(self.dirs), m,
-                                                L.ptr(self.buffer), self.buffer.numel() * 8, L.stream_ptr()))
-
-    def matches(self, grid, settings, dirs):
-        return (self.key == (tuple(map(float, grid.box.ravel())), tuple(map(int, grid.resolution)),
-                             settings.observer, settings.dr, settings.n_steps)
-                and dirs.data_ptr() == self.dirs.data_ptr() and dirs.shape[0] == self.dirs.shape[0])
-
-
 def los_integrate(grid, settings, dirs, B, ne=None, cre=None, n_real=1,
-                  want=('dm', 'fd', 'I', 'Q', 'U'), out=None, out_layout=None, geometry=None):
+                  want=('dm', 'fd', 'I', 'Q', 'U'), out=None, out_layout=None):
     """
     Integrate every realisation along `dirs` [m,3] (imb_los_integrate).  Returns a dict of
     [n_real, m] tensors for the requested quantities.  With `out_layout = (cols_per_dest,
@@ -239,11 +212,6 @@ def los_integrate(grid, settings, dirs, B, ne=None, cre=None, n_real=1,
                 res[k] = torch.empty((n_real, m), dtype=torch.float64, device=B.device)
     cfg = settings.c_struct(*(out_layout or (0, 0)))
     interleaved = B.dim() == 4                      # realisation-interleaved layouts (b_shape)
-    if geometry is not None and interleaved:
-        if not geometry.matches(grid, settings, dirs):
-            raise ValueError('the LosGeometry cache was built for another grid / sampling / direction set')
-        cfg.geometry = geometry.buffer.data_ptr()
-        cfg.geometry_bytes = geometry.buffer.numel() * 8
     L.check(L.load().imb_los_integrate(
         C.byref(grid.c), C.byref(cfg), L.ptr(dirs), m, L.ptr(B),
         n_real if interleaved else B.shape[0], b_stride_of(B),

@@ -112,7 +112,7 @@ class PeerExchange:
 
 class EnsembleEvaluator:
     def __init__(self, box, resolution, nside, los_settings, quantities=('fd', 'dm', 'I', 'Q', 'U'),
-                 n_real=1, rank=0, world=1, b_stride='auto', group=None, exchange='auto', cache_geometry=True):
+                 n_real=1, rank=0, world=1, b_stride='auto', group=None, exchange='auto'):
         import torch
         self.torch = torch
         self.grid = engine.DeviceGrid(box, resolution)
@@ -127,9 +127,6 @@ class EnsembleEvaluator:
         self.n_local = self.hi - self.lo
         self.b_stride = engine.pick_b_stride(self.n_local) if b_stride == 'auto' else int(b_stride)
         self.dirs = engine.healpix_ring_dirs(self.nside)
-        # per-sample geometry of the ray march, built once (0.08 * m * n_steps kB): the parameter points of
-        # a sampler run share grid, observer and directions
-        self.geometry = engine.LosGeometry(self.grid, self.settings, self.dirs) if cache_geometry else None
         self._field_bufs = {}
         self._local = None                          # world = 1 evaluator of evaluate_points
         self.library_collectives = False            # True: all-reduces through imb_comm_* instead of torch
@@ -218,7 +215,7 @@ class EnsembleEvaluator:
         return engine.los_integrate(self.grid, self.settings, self.dirs, fields['magnetic_field'],
                                     fields.get('thermal_electron_density'),
                                     fields.get('cosmic_ray_electron_density'), n_real=self.n_local,
-                                    want=want, out=out, out_layout=layout, geometry=self.geometry)
+                                    want=want, out=out, out_layout=layout)
 
     def simulate(self, descs, seeds):
         """Run fields + LOS for this rank's block of realisations (outputs stay in device buffers)."""

@@ -95,13 +95,6 @@ typedef struct {
   int32_t n_peers;
   int32_t reserved;
   int64_t peer_delta[16];
-  /* Optional geometry cache (realisation-interleaved layouts only): a device buffer of             */
-  /* imb_los_geometry_bytes(m, n_steps) bytes filled by imb_los_geometry_build with THE SAME grid,   */
-  /* observer, dr, n_steps and directions.  The per-sample geometry of the ray march (trilinear      */
-  /* weights, cell, vertex-load mask) depends on those only -- not on the fields -- so a sampler     */
-  /* that evaluates thousands of parameter points builds it once.  NULL: computed on the fly.        */
-  const void* geometry;
-  int64_t geometry_bytes;
 } imb_los_cfg;
 
 /* ---- likelihood options ------------------------------------------------------------ */
@@ -187,13 +180,6 @@ int imb_los_integrate(const imb_grid* grid, const imb_los_cfg* cfg,
                       double* out_dm, double* out_fd,
                       double* out_I, double* out_Q, double* out_U, void* stream);
 
-/*
- * Geometry cache of the ray march (see imb_los_cfg.geometry): 80 bytes per (pixel, radial step).
- * imb_los_geometry_build fills `cache` for `m` directions; asynchronous on `stream`.
- */
-int64_t imb_los_geometry_bytes(int m, int n_steps);
-int imb_los_geometry_build(const imb_grid* grid, const imb_los_cfg* cfg, const double* dirs, int m,
-                           void* cache, int64_t cache_bytes, void* stream);
 
 
 /* PI = sqrt(Q^2+U^2), PA = atan2(U,Q)/2 (keys 'PI','PA', observable_dict.py:15-20) */

@@ -53,7 +53,7 @@ def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_lib.Grid) == 64
     assert C.sizeof(_lib.FieldDesc) == 208
-    assert C.sizeof(_lib.LosCfg) == 248
+    assert C.sizeof(_lib.LosCfg) == 232
 
 
 def test_field_layout_selection_host_only(lib):

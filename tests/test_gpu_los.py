@@ -206,23 +206,3 @@ def test_edge_cases_empty_and_all_outside(eng):
     out = eng.los_integrate(grid, eng.LosSettings(n_steps=0), away, f['magnetic_field'],
                             f['thermal_electron_density'], None, n_real=2, want=('dm', 'fd'))
     assert all(bool((t == 0).all()) for t in out.values())
-
-
-@pytest.mark.parametrize('bs,N', [(96, 33), (48, 16), (24, 5)])
-def test_geometry_cache_gives_identical_maps(eng, bs, N):
-    """imb_los_geometry_build: the cached weights / cells / load masks are the ones phase A computes, so the
-    maps are bit-identical with and without the cache (every layout, padded groups, ray segments)."""
-    import torch
-    grid = eng.DeviceGrid(BOX, [20, 18, 12])
-    f = eng.field_eval(grid, DESCS, list(range(7, 7 + N)), b_stride=bs)
-    dirs = eng.healpix_ring_dirs(4)
-    cfg = eng.LosSettings(dr=0.2)
-    args = (grid, cfg, dirs, f['magnetic_field'], f['thermal_electron_density'], f['cosmic_ray_electron_density'])
-    plain = eng.los_integrate(*args, n_real=N)
-    geo = eng.LosGeometry(grid, cfg, dirs)
-    cached = eng.los_integrate(*args, n_real=N, geometry=geo)
-    for k in KEYS:
-        assert torch.equal(plain[k], cached[k]), k
-    other = eng.healpix_ring_dirs(2)
-    with pytest.raises(ValueError):
-        eng.los_integrate(grid, cfg, other, *args[3:], n_real=N, geometry=geo)

@@ -20,7 +20,6 @@ def main():
     ap.add_argument('--reps', type=int, default=20)
     ap.add_argument('--once', action='store_true', help='one warm-up + one launch (ncu captures)')
     ap.add_argument('--b-stride', default='auto')
-    ap.add_argument('--no-geometry-cache', action='store_true')
     args = ap.parse_args()
     import torch
     from imagine_b200 import _lib, engine
@@ -32,7 +31,7 @@ def main():
     settings = engine.LosSettings(**bench.LOS_KW)
     bs = args.b_stride if args.b_stride == 'auto' else int(args.b_stride)
     ev = EnsembleEvaluator(bench.BOX, [w['G']] * 3, w['nside'], settings, w['quantities'], n_real=N,
-                           exchange='allgather', b_stride=bs, cache_geometry=not args.no_geometry_cache)
+                           exchange='allgather', b_stride=bs)
     descs = bench.field_descs(w['quantities'])
     f = ev.fields(descs, bench.ensemble_seeds(N))
     ev.los(f)
