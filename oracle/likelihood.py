@@ -115,6 +115,53 @@ def ensemble_loglike_gram(sims, meas, var, estimator='oas'):
     return float(-0.5 * (quad + sign_d * sign_k * logdet))
 
 
+def ensemble_loglike_gram_extended(sims, meas, var, estimator='oas'):
+    """
+    The Gram route evaluated in EXTENDED precision (np.longdouble: 64-bit mantissa on x86) wherever a long
+    reduction is involved, as a comparator for absolute-tolerance tests at full size: at |log L| ~ 10^6-10^7 a
+    double carries only ~2e-9, so a float64 NumPy comparator is itself uncertain at the 1e-8 level.  The
+    N x N solve runs in float64 on matrices rounded from extended precision (condition number ~ 1 + O(1)).
+    O(m N^2) longdouble operations: seconds at m = 49 152, N = 64.
+    """
+    ld = np.longdouble
+    n, m = sims.shape
+    x = np.asarray(sims, dtype=ld)
+    meas = np.asarray(meas, dtype=ld).reshape(-1)
+    var = np.asarray(var, dtype=ld).reshape(-1)
+    mean = x.sum(axis=0) / ld(n)
+    u = x - mean
+    g = np.zeros((n, n), dtype=ld)
+    for i in range(n):
+        g[i, :i + 1] = (u[:i + 1] * u[i]).sum(axis=1)
+        g[:i + 1, i] = g[i, :i + 1]
+    if estimator == 'oas':
+        trs = np.trace(g) / ld(n)
+        trs2 = (g * g).sum() / ld(n * n)
+        num = (ld(1) - ld(2) / ld(m)) * trs2 + trs * trs
+        den = (ld(n) + ld(1) - ld(2) / ld(m)) * (trs2 - trs * trs / ld(m))
+        rho = ld(1) if den == 0 else min(ld(1), num / den)
+    elif estimator == 'empirical':
+        trs, rho = ld(0), ld(0)
+    else:
+        raise ValueError(estimator)
+    dvec = var + rho * trs / ld(m)
+    d = meas - mean
+    c = (ld(1) - rho) / ld(n)
+    ud = u / dvec
+    gw = np.zeros((n, n), dtype=ld)
+    for i in range(n):
+        gw[i, :i + 1] = (ud[:i + 1] * u[i]).sum(axis=1)
+        gw[:i + 1, i] = gw[i, :i + 1]
+    y = (ud * d).sum(axis=1)
+    kmat = (np.eye(n, dtype=ld) + c * gw).astype(np.float64)
+    sign_k, logdet_k = np.linalg.slogdet(kmat)
+    z = np.linalg.solve(kmat, y.astype(np.float64))
+    sign_d = np.sign(dvec).prod()
+    logdet = np.log(np.abs(dvec) * ld(2) * ld(np.pi)).sum() + ld(logdet_k)
+    quad = (d / dvec * d).sum() - c * (y * z.astype(ld)).sum()
+    return float(ld(-0.5) * (quad + sign_d * ld(sign_k) * logdet))
+
+
 def ensemble_diagonal_loglike(sims, meas, cov):
     meas = np.asarray(meas, dtype=np.float64).reshape(1, -1)
     diff = meas - pmean(sims)

@@ -83,9 +83,15 @@ def test_c3_likelihood_gram_vs_numpy_gram_and_sharding_invariance(c3):
         meas[q] = (t[0] * 1.003 + sigma).contiguous()
         var[q] = torch.full((49152,), sigma ** 2, dtype=torch.float64, device='cuda')
     got = ev.loglike(maps, meas, var)
+    total_ext = 0.0
     for q, t in maps.items():
-        total_np += OK.ensemble_loglike_gram(t.cpu().numpy(), meas[q].cpu().numpy(), var[q].cpu().numpy())
+        args = (t.cpu().numpy(), meas[q].cpu().numpy(), var[q].cpu().numpy())
+        total_np += OK.ensemble_loglike_gram(*args)
+        total_ext += OK.ensemble_loglike_gram_extended(*args)
     assert abs(got - total_np) <= 1e-8 * max(1.0, abs(total_np) * 1e-6), (got, total_np)
+    # |log L| ~ 2e6 here: one ulp is 2.3e-10; against the extended-precision Gram route the GPU value holds
+    # north_star's 1e-8 ABSOLUTE (the float64 NumPy comparator above is itself only good to a few 1e-9)
+    assert abs(got - total_ext) <= 1e-8, (got, total_ext, got - total_ext)
     # simulating the ensemble in two halves (what 2 ranks do) gives bit-identical maps
     from imagine_b200.hotpath import EnsembleEvaluator
     for rank in (0, 1):

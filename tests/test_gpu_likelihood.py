@@ -135,6 +135,22 @@ def test_gram_route_at_scale_vs_oracle_gram(eng, N, m):
         assert abs(got - want) <= 1e-8 * max(1.0, abs(want) * 1e-4), (got, want)
 
 
+@pytest.mark.parametrize('N,m', [(16, 3072), (64, 12288), (64, 49152)])
+def test_gram_route_1e8_absolute_vs_extended_precision(eng, N, m):
+    """north_star's tolerance, 1e-8 ABSOLUTE, at the sizes of C2 / C3 where |log L| ~ 10^5-10^6: the comparator
+    is the Gram route in extended precision (oracle/likelihood.py:ensemble_loglike_gram_extended), because a
+    float64 NumPy evaluation is itself only good to a few 1e-9 there (the looser bound of the test above)."""
+    rng = np.random.default_rng(N + m)
+    base = 30 * rng.normal(size=m)
+    sims = base + 8 * rng.normal(size=(N, m))
+    meas = base + 8 * rng.normal(size=m)
+    var = rng.uniform(0.05, 0.2, size=m)
+    got = eng.loglike_ensemble(_dev(sims), _dev(meas), _dev(var), estimator='oas')
+    want = OK.ensemble_loglike_gram_extended(sims, meas, var, estimator='oas')
+    assert abs(want) > 1e4
+    assert abs(got - want) <= 1e-8, (got, want, got - want)
+
+
 @pytest.mark.parametrize('N,m', [(16, 768), (8, 1500)])
 def test_dense_vs_gram_vs_reference_algebra(eng, N, m):
     """Dense DMMA + Cholesky route == Gram route == NumPy dense LU (the reference algebra)."""
