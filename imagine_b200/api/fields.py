@@ -80,7 +80,14 @@ class _DeviceFieldMixin:
                 try:
                     p = p.to_value(unit)
                 except Exception:            # e.g. 1/kpc given where rad/kpc is expected
-                    p = p.to_value(unit, u.dimensionless_angles())
+                    try:
+                        p = p.to_value(unit, u.dimensionless_angles())
+                    except Exception:
+                        # FieldFactory wraps bare numbers as dimensionless Quantities
+                        # (field_factory.py:210): a bare number means "in canonical units"
+                        if p.unit != u.dimensionless_unscaled:
+                            raise
+                        p = p.value
             vals.append(float(p))
         return vals
 

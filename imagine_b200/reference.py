@@ -20,6 +20,9 @@ Resolution order of :func:`ensure_imagine`:
    back ends never called here   ``pymultinest``, ``ultranest``, ``dynesty``, ``emcee``,
                                  ``hampyx``, ``corner``, ``cmasher``, ``schwimmbad``, ...)
    ``numpy.int``                 alias of ``int`` (``fields/grid.py:59`` predates NumPy 1.24)
+   ``ensemble_seed_generator``   ``tools/random_seed.py:60`` evaluates ``np.uint32(-1)//3``, which
+                                 NumPy >= 2 refuses; replaced by the same draw with the literal bound
+                                 1431655765 (identical seeds under NumPy 1)
    ============================  =========================================================
 
    Only ABSENT modules are replaced; anything installed is left alone.
@@ -145,6 +148,7 @@ def ensure_imagine():
         return sys.modules['imagine']
     try:
         import imagine                                  # noqa: F401
+        _patch_numpy2(imagine)
         _STATE['backend'], _STATE['root'] = 'installed', os.path.dirname(os.path.dirname(imagine.__file__))
         return imagine
     except Exception:
@@ -165,8 +169,27 @@ def ensure_imagine():
             imagine = importlib.import_module('imagine')
     finally:
         sys.path.remove(root)
+    _patch_numpy2(imagine)
     _STATE['backend'], _STATE['root'] = 'sources+standins', root
     return imagine
+
+
+def _patch_numpy2(imagine):
+    """tools/random_seed.py:60 under NumPy >= 2: same draw, literal bound (= np.uint32(-1) // 3)."""
+    import numpy as np
+    try:
+        np.uint32(-1)
+        return
+    except OverflowError:
+        pass
+
+    def ensemble_seed_generator(size):
+        return np.random.randint(low=1, high=1431655765, size=int(size))
+    ensemble_seed_generator.__doc__ = 'imagine.tools.random_seed.ensemble_seed_generator with the literal bound'
+    for name in ('imagine.tools.random_seed', 'imagine.tools', 'imagine.pipelines.pipeline'):
+        mod = sys.modules.get(name)
+        if mod is not None and hasattr(mod, 'ensemble_seed_generator'):
+            mod.ensemble_seed_generator = ensemble_seed_generator
 
 
 def backend():
