@@ -152,7 +152,15 @@ los_rl_kernel(const __grid_constant__ RlArgs ra) {
   constexpr unsigned int GEO = sizeof(RlGeo);
   static_assert(sizeof(RlGeo) == 112, "RlGeo layout is addressed by byte offsets below");
   __shared__ RlPix s_pix;
-  __shared__ RlGeo s_geo[S * CH + 1];        // [segment][step]; + 1: the march reads one step slot ahead
+  // [segment][step]; + 1: the march reads one step slot ahead.  With several segments per warp every
+  // segment's slots are 16 bytes further round the banks, so the quarter / half warps of one 128-bit
+  // read hit different banks (CH * 112 bytes is a multiple of 128: 4-way conflicts without the pad,
+  // 18 M of the 35 M shared-load wavefronts at 8 realisations per group)
+  constexpr unsigned int SEG_BYTES = CH * GEO + (S > 1 ? 16 : 0);
+  __shared__ __align__(16) unsigned char s_geo_raw[S * SEG_BYTES + GEO];
+  auto geo_at = [&](int sg, int i) -> RlGeo& {
+    return *reinterpret_cast<RlGeo*>(s_geo_raw + sg * SEG_BYTES + i * GEO);
+  };
   __shared__ double s_var[VAR_P ? S * CH : 1][3];
   __shared__ double s_dm[G][32];             // shared-n_e dispersion measure, per warp and lane (see phase B)
   __shared__ int2 s_rng[G];                  // first / last in-box step among those each warp prepared
@@ -209,7 +217,7 @@ los_rl_kernel(const __grid_constant__ RlArgs ra) {
   constexpr long long CS = 3 * RL;                       // doubles per vertex of the wide layout
   const double* __restrict__ Bg = a.B + (long long)(active ? g : 0) * a.g.ncell * CS + rl;
   // shared-memory byte address of this lane group's (segment's) first step slot
-  const unsigned int geo_seg = (unsigned int)__cvta_generic_to_shared(&s_geo[seg * CH]);
+  const unsigned int geo_seg = (unsigned int)__cvta_generic_to_shared(&geo_at(seg, 0));
 
   const double st = pc.st, ct = pc.ct, cp = pc.cp, sp = pc.sp;
   // the Faraday depth is carried as the rotation angle 2 lambda^2 phi when it rotates anything
@@ -269,7 +277,7 @@ los_rl_kernel(const __grid_constant__ RlArgs ra) {
         code |= (qx << 8) | (qy << 9) | (qz << 10) | (1 << 11);
       }
       // the slot of parity s along an axis holds the vertex i (weight 1 - t) when s == i & 1, else i + 1 (t)
-      RlGeo& ge = s_geo[seg * CH + istep];
+      RlGeo& ge = geo_at(seg, istep);
       const double wx[2] = {qx ? cc.tx : 1.0 - cc.tx, qx ? 1.0 - cc.tx : cc.tx};
       const double wy[2] = {qy ? cc.ty : 1.0 - cc.ty, qy ? 1.0 - cc.ty : cc.ty};
       const double wz[2] = {qz ? cc.tz : 1.0 - cc.tz, qz ? 1.0 - cc.tz : cc.tz};
@@ -305,7 +313,7 @@ los_rl_kernel(const __grid_constant__ RlArgs ra) {
       // is (the maps of a realisation must not depend on how the ensemble is sharded, bit for bit)
       double acc = s_dm[warp][lane];
 #pragma unroll
-      for (int w = 0; w < G; ++w) acc += s_geo[seg * CH + w * RL + rl].dm;
+      for (int w = 0; w < G; ++w) acc += geo_at(seg, w * RL + rl).dm;
       s_dm[warp][lane] = acc;
     }
 #ifdef IMB_LOS_DBG_ONLYA

@@ -44,6 +44,14 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    if not args.once:
+        seeds = bench.ensemble_seeds(N)
+        e0.record()
+        for _ in range(reps):
+            ev.fields(descs, seeds)
+        e1.record()
+        torch.cuda.synchronize()
+        print('fields_ms %.4f' % (e0.elapsed_time(e1) / reps))
     chk = {q: float(ev.local_maps[q].double().abs().sum()) for q in w['quantities']}
     print('los_ms %.4f  b_stride %s  n_real %d  checksum %s' % (ms, ev.b_stride, N, chk))
 
