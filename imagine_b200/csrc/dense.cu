@@ -7,6 +7,7 @@
 //   input (the reference is LU throughout and its tests feed np.random.rand matrices,
 //   tests/test_likelihood.py:63-113) takes a partially pivoted LU instead.
 // Reference arithmetic: oracle/likelihood.py (empirical_mcov / oas_mcov / ensemble_loglike).
+#include <vector>
 #include "common.cuh"
 #include "linalg.cuh"
 
@@ -89,66 +90,107 @@ __global__ void symmetry_kernel(const double* __restrict__ A, int m, int ld, int
 }
 
 // ---- blocked Cholesky (lower, in place, row-major, ld = m; rows 0..m, row m = rhs) ----------
-// factor the kb x kb diagonal tile at k0; pivots[k0+k] = value under the square root
+// factor the kb x kb diagonal tile at k0; pivots[k0+k] = value under the square root.
+// The tile is reduced in its L D L^T form -- column k keeps t_ik = l_ik l_kk and the update is
+// T[i][j] -= t_ik (t_jk / p_k) -- so that the serial chain of a step is ONE division, no square root and
+// one barrier (sqrt + divide + two barriers per step made this kernel 17 % of the factorisation);
+// L = T / sqrt(p) column by column falls out at the end, in parallel.  256 threads = 4 row groups x 64
+// columns, no index divisions.
 __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ A, int ld, int k0, int kb,
                                                     double* __restrict__ pivots, int* __restrict__ info) {
   __shared__ double T[TB][TB + 1];
-  const int tid = threadIdx.x;
-  for (int e = tid; e < kb * kb; e += 256) {
-    const int i = e / kb, j = e % kb;
-    T[i][j] = A[(size_t)(k0 + i) * ld + k0 + j];
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+  for (int i = ty; i < kb; i += 4)
+    if (tx < kb) T[i][tx] = A[(size_t)(k0 + i) * ld + k0 + tx];
+  __syncthreads();
+  for (int k = 0; k + 1 < kb; ++k) {
+    if (tx > k && tx < kb) {
+      const double u = T[tx][k] / T[k][k];
+      // rows k + 1 + ty + 4 q of column tx, diagonal and below: all loads, then all stores
+      const int ib = k + 1 + ty;
+      double tik[TB / 4], tv[TB / 4];
+#pragma unroll
+      for (int q = 0; q < TB / 4; ++q) {
+        const int i = ib + 4 * q;
+        const bool ok = i < kb && i >= tx;
+        tik[q] = ok ? T[i][k] : 0.0;
+        tv[q] = ok ? T[i][tx] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < TB / 4; ++q) {
+        const int i = ib + 4 * q;
+        if (i < kb && i >= tx) T[i][tx] = tv[q] - tik[q] * u;
+      }
+    }
+    __syncthreads();          // column k + 1 (and its pivot) is final
+  }
+  __shared__ int s_bad;
+  if (tid == 0) s_bad = 0x7fffffff;
+  __syncthreads();
+  if (tx < kb) {
+    const double p = T[tx][tx];
+    const double lkk = sqrt(p);
+    if (ty == 0) {
+      pivots[k0 + tx] = p;
+      if (!(p > 0.0)) atomicMin(&s_bad, k0 + tx + 1);
+    }
+    for (int i = tx + ty; i < kb; i += 4)
+      A[(size_t)(k0 + i) * ld + k0 + tx] = (i == tx) ? lkk : T[i][tx] / lkk;
   }
   __syncthreads();
-  for (int k = 0; k < kb; ++k) {
-    if (tid == 0) {
-      const double p = T[k][k];
-      pivots[k0 + k] = p;
-      if (!(p > 0.0) && *info == 0) *info = k0 + k + 1;
-      T[k][k] = sqrt(p);
-    }
-    __syncthreads();
-    const double lkk = T[k][k];
-    for (int i = k + 1 + tid; i < kb; i += 256) T[i][k] /= lkk;
-    __syncthreads();
-    const int rem = kb - k - 1;
-    for (int e = tid; e < rem * rem; e += 256) {
-      const int i = k + 1 + e / rem, j = k + 1 + e % rem;
-      if (j <= i) T[i][j] -= T[i][k] * T[j][k];
-    }
-    __syncthreads();
-  }
-  for (int e = tid; e < kb * kb; e += 256) {
-    const int i = e / kb, j = e % kb;
-    if (j <= i) A[(size_t)(k0 + i) * ld + k0 + j] = T[i][j];
-  }
+  // info[0] keeps the FIRST non-positive pivot of the whole factorisation (LAPACK's info)
+  if (tid == 0 && s_bad != 0x7fffffff && *info == 0) *info = s_bad;
 }
 
-// rows i in [k0+kb, nrows): A[i, k0:k0+kb] <- A[i, k0:k0+kb] * L11^-T ; 64 rows per block
+// rows i in [k0+kb, nrows): A[i, k0:k0+kb] <- A[i, k0:k0+kb] * L11^-T ; 64 rows per block, a row per
+// thread.  The row lives in registers (the substitution is fully unrolled), L11 is read as shared-memory
+// broadcasts, and every dot product runs on two independent FMA chains (DFMA latency is 8 cycles and a
+// block is two warps: the chain length is the run time; the diagonal is applied as a reciprocal for the
+// same reason).  kb < 64: L11 is padded with the identity.
 __global__ void __launch_bounds__(64) trsm_kernel(double* __restrict__ A, int ld, int k0, int kb,
                                                   int nrows) {
-  extern __shared__ double sm[];
-  double (*L)[TB + 1] = reinterpret_cast<double (*)[TB + 1]>(sm);
-  double (*R)[TB + 1] = reinterpret_cast<double (*)[TB + 1]>(sm + TB * (TB + 1));
+  extern __shared__ __align__(16) double sm[];
+  double (*L)[TB] = reinterpret_cast<double (*)[TB]>(sm);
+  double (*R)[TB + 1] = reinterpret_cast<double (*)[TB + 1]>(sm + TB * TB);
   const int tid = threadIdx.x;
   const int r0 = k0 + kb + blockIdx.x * TB;
-  for (int e = tid; e < kb * kb; e += 64) {
-    const int i = e / kb, j = e % kb;
-    L[i][j] = A[(size_t)(k0 + i) * ld + k0 + j];
+  __shared__ double rdiag[TB];
+  // row e / 64 per iteration, 64 contiguous doubles across the block; 16 independent loads in flight
+#pragma unroll 16
+  for (int e = tid; e < TB * TB; e += 64) {
+    const int i = e >> 6, j = e & 63;
+    double v = (i == j) ? 1.0 : 0.0;
+    if (i < kb && j <= i) v = A[(size_t)(k0 + i) * ld + k0 + j];
+    L[i][j] = v;
   }
-  for (int e = tid; e < TB * kb; e += 64) {
-    const int i = e / kb, j = e % kb;
-    R[i][j] = (r0 + i < nrows) ? A[(size_t)(r0 + i) * ld + k0 + j] : 0.0;
+#pragma unroll 16
+  for (int e = tid; e < TB * TB; e += 64) {
+    const int i = e >> 6, j = e & 63;
+    R[i][j] = (r0 + i < nrows && j < kb) ? A[(size_t)(r0 + i) * ld + k0 + j] : 0.0;
   }
   __syncthreads();
-  for (int c = 0; c < kb; ++c) {
-    double s = R[tid][c];
-    for (int j = 0; j < c; ++j) s -= R[tid][j] * L[c][j];
-    R[tid][c] = s / L[c][c];
-  }
+  rdiag[tid] = 1.0 / L[tid][tid];          // 64 divisions off the substitution's serial chain
   __syncthreads();
-  for (int e = tid; e < TB * kb; e += 64) {
-    const int i = e / kb, j = e % kb;
-    if (r0 + i < nrows) A[(size_t)(r0 + i) * ld + k0 + j] = R[i][j];
+  double r[TB];
+#pragma unroll
+  for (int c = 0; c < TB; ++c) r[c] = R[tid][c];
+#pragma unroll
+  for (int c = 0; c < TB; ++c) {
+    double s0 = r[c], s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j + 1 < c; j += 2) {
+      s0 = fma(-r[j], L[c][j], s0);
+      s1 = fma(-r[j + 1], L[c][j + 1], s1);
+    }
+    if (c & 1) s0 = fma(-r[c - 1], L[c][c - 1], s0);
+    r[c] = (s0 + s1) * rdiag[c];
+  }
+#pragma unroll
+  for (int c = 0; c < TB; ++c) R[tid][c] = r[c];
+  __syncthreads();
+  for (int e = tid; e < TB * TB; e += 64) {
+    const int i = e >> 6, j = e & 63;
+    if (r0 + i < nrows && j < kb) A[(size_t)(r0 + i) * ld + k0 + j] = R[i][j];
   }
 }
 
@@ -183,6 +225,102 @@ __global__ void __launch_bounds__(256) chol_update_kernel(double* __restrict__ A
       const int j = j0 + nb * 8 + 2 * (lane & 3) + h;
       if (j < m && j <= i) A[(size_t)i * ld + j] -= acc[nb][h];
     }
+}
+
+// The same update on 128 x 128 tiles for even ld and K a multiple of 16 (every panel but a ragged last
+// one): the two 128 x 16 operand chunks of a k-step arrive by 16-byte cp.async (LDGSTS) into a double
+// ring (3 stages) whose rows keep the k index contiguous, exactly as the panel lies in memory -- no transposing
+// 8-byte stores (the 64-tile kernel above spends its L1 data pipe on them: ncu r02, 77 % of the
+// wavefront peak at 43 % DMMA) -- and a row stride of 20 doubles makes the DMMA fragment reads
+// conflict-free.  Warp (wi, wj) of the 4 x 4 warp grid owns 32 rows x 32 columns: 4 A fragments and
+// 4 B fragments feed 16 DMMAs per 4-deep k-step (8 shared loads per 16 tensor instructions instead
+// of 9 per 8); 16 warps per SM keep the tensor pipe fed across the fixed issue gaps of a DMMA chain
+// (8 warps of 32 x 64: 60 % DMMA-active).
+constexpr int UT = 128;            // tile edge
+constexpr int UK = 16;             // k-chunk
+constexpr int UKS = UK + 4;        // shared row stride in doubles
+constexpr int UST = 3;             // cp.async stages
+constexpr size_t UPD_SMEM = sizeof(double) * 2 * UST * UT * UKS;   // operands x stages
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+
+constexpr int UTHREADS = 512;      // 16 warps: 4 x 4 warp grid, 32 x 32 outputs per warp
+__global__ void __launch_bounds__(UTHREADS, 1) chol_update128_kernel(double* __restrict__ A, int ld, int k0, int K,
+                                                                     int t0, int nrows, int jmax) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  extern __shared__ __align__(16) double usm[];
+  double (*sA)[UT][UKS] = reinterpret_cast<double (*)[UT][UKS]>(usm);
+  double (*sB)[UT][UKS] = reinterpret_cast<double (*)[UT][UKS]>(usm + UST * UT * UKS);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wi = warp >> 2, wj = warp & 3, fr = lane >> 2, fk = lane & 3;
+  const int i0 = t0 + bi * UT, j0 = t0 + bj * UT;
+  double acc[4][4][2];
+#pragma unroll
+  for (int ra = 0; ra < 4; ++ra)
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) acc[ra][nb][0] = acc[ra][nb][1] = 0.0;
+
+  auto stage = [&](int c, int buf) {
+#pragma unroll
+    for (int q = 0; q < UT * 8 / UTHREADS; ++q) {
+      const int p = tid + UTHREADS * q, row = p >> 3, seg = (p & 7) * 2;
+      const int ri = i0 + row, rj = j0 + row;
+      const bool okA = ri < nrows, okB = rj < jmax;
+      // out-of-range rows are zero-filled (src-size 0); the address stays a valid one
+      cp_async16(&sA[buf][row][seg], A + (size_t)(okA ? ri : t0) * ld + k0 + c * UK + seg, okA ? 16 : 0);
+      cp_async16(&sB[buf][row][seg], A + (size_t)(okB ? rj : t0) * ld + k0 + c * UK + seg, okB ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // chunk c + 2 is requested right after the barrier that ends the compute of chunk c - 1 (whose buffer
+  // it takes): one barrier per chunk, two chunks in flight during the DMMAs
+  const int nch = K / UK;
+  stage(0, 0);
+  if (nch > 1) stage(1, 1);
+  for (int c = 0; c < nch; ++c) {
+    const int buf = c % UST;
+    if (c + 1 < nch) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (c + 2 < nch) stage(c + 2, (c + 2) % UST);
+#pragma unroll
+    for (int kk = 0; kk < UK; kk += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int ra = 0; ra < 4; ++ra) a[ra] = sA[buf][32 * wi + 8 * ra + fr][kk + fk];
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) b[nb] = sB[buf][32 * wj + 8 * nb + fr][kk + fk];
+#pragma unroll
+      for (int ra = 0; ra < 4; ++ra)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) dmma884(acc[ra][nb][0], acc[ra][nb][1], a[ra], b[nb]);
+    }
+  }
+
+#pragma unroll
+  for (int ra = 0; ra < 4; ++ra) {
+    const int i = i0 + 32 * wi + 8 * ra + fr;
+    if (i >= nrows) continue;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      const int j = j0 + 32 * wj + 8 * nb + 2 * fk;
+      double* p = A + (size_t)i * ld + j;
+      if (j + 1 < jmax && j + 1 <= i) {            // both elements in the lower triangle: one 16-byte RMW
+        double2 v = *reinterpret_cast<double2*>(p);
+        v.x -= acc[ra][nb][0];
+        v.y -= acc[ra][nb][1];
+        *reinterpret_cast<double2*>(p) = v;
+      } else {
+        if (j < jmax && j <= i) p[0] -= acc[ra][nb][0];
+        if (j + 1 < jmax && j + 1 <= i) p[1] -= acc[ra][nb][1];
+      }
+    }
+  }
 }
 
 // ---- partially pivoted LU on the augmented matrix [A | d] (ld = m + 1) ------------------------
@@ -361,28 +499,84 @@ static int build_matrix(const double* sims, int N, int m, const double* cov, int
   return IMB_OK;
 }
 
+// trailing update A[i][j] -= sum_{k < K} A[i][k0+k] A[j][k0+k] for i in [t0, nrows), j in [t0, jmax), j <= i
+static int launch_update(double* A, int ld, int k0, int K, int t0, int nrows, int jmax, cudaStream_t s) {
+  if (t0 >= jmax || t0 >= nrows || K <= 0) return IMB_OK;
+  if (ld % 2 == 0 && K % UK == 0) {
+    const int nty = (nrows - t0 + UT - 1) / UT, ntx = (jmax - t0 + UT - 1) / UT;
+    chol_update128_kernel<<<dim3(ntx, nty), UTHREADS, UPD_SMEM, s>>>(A, ld, k0, K, t0, nrows, jmax);
+  } else {
+    const int nty = (nrows - t0 + TB - 1) / TB, ntx = (jmax - t0 + TB - 1) / TB;
+    chol_update_kernel<<<dim3(ntx, nty), 256, 0, s>>>(A, ld, k0, K, t0, nrows, jmax);
+  }
+  IMB_LAUNCHED();
+  return IMB_OK;
+}
+
+// Two-level right-looking factorisation with one block column of lookahead.
+//   * 64-wide panels (tile factor + triangular solve) update only the rest of their 256-wide block
+//     column; the trailing matrix is read and written once per BLOCK COLUMN, by a rank-256 update (a
+//     quarter of the passes over the matrix, and 256 k-steps of DMMA per tile visit).
+//   * The rank-256 update of block column b is split: the next block column first ("head"), then
+//     everything to its right ("rest").  The panel chain of block column b + 1 (latency-bound: one small
+//     block, then a few dozen) runs on a second, high-priority stream as soon as the head is done and
+//     overlaps the rest update, which only touches columns further right.
+constexpr int OB = 256;
+struct Lookahead {
+  cudaStream_t panel = nullptr;
+  std::vector<cudaEvent_t> ev;
+  int get(size_t n) {
+    if (!panel) {
+      int lo = 0, hi = 0;
+      IMB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      IMB_CUDA(cudaStreamCreateWithPriority(&panel, cudaStreamNonBlocking, hi));
+    }
+    while (ev.size() < n) {
+      cudaEvent_t e;
+      IMB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ev.push_back(e);
+    }
+    return IMB_OK;
+  }
+};
+
 static int cholesky(DenseWs& w, int m, cudaStream_t s) {
   const int ld = m, nrows = m + 1;
   static bool attr_set = false;
-  const size_t trsm_smem = sizeof(double) * 2 * TB * (TB + 1);
+  static Lookahead la;
+  const size_t trsm_smem = sizeof(double) * (TB * TB + TB * (TB + 1));
   if (!attr_set) {
     IMB_CUDA(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem));
+    IMB_CUDA(cudaFuncSetAttribute(chol_update128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)UPD_SMEM));
     attr_set = true;
   }
-  for (int k0 = 0; k0 < m; k0 += TB) {
-    const int kb = (m - k0) < TB ? (m - k0) : TB;
-    potf2_kernel<<<1, 256, 0, s>>>(w.A, ld, k0, kb, w.pivots, w.info);
-    IMB_LAUNCHED();
-    const int t0 = k0 + kb;
-    const int rows_below = nrows - t0;
-    if (rows_below <= 0) break;
-    trsm_kernel<<<(rows_below + TB - 1) / TB, 64, trsm_smem, s>>>(w.A, ld, k0, kb, nrows);
-    IMB_LAUNCHED();
-    if (t0 < m) {
-      const int nty = (nrows - t0 + TB - 1) / TB, ntx = (m - t0 + TB - 1) / TB;
-      chol_update_kernel<<<dim3(ntx, nty), 256, 0, s>>>(w.A, ld, k0, kb, t0, nrows, m);
+  const int nblk = (m + OB - 1) / OB;
+  IMB_TRY(la.get(2 * (size_t)nblk + 1));
+  cudaStream_t sp = la.panel;
+  // events: [2 b] panel chain of block column b done (on sp), [2 b + 1] head update of b done (on s)
+  IMB_CUDA(cudaEventRecord(la.ev[2 * nblk], s));             // everything queued on s before this call
+  IMB_CUDA(cudaStreamWaitEvent(sp, la.ev[2 * nblk], 0));
+  for (int b = 0; b < nblk; ++b) {
+    const int K0 = b * OB;
+    const int kend = (m - K0) < OB ? m : K0 + OB;
+    if (b > 0) IMB_CUDA(cudaStreamWaitEvent(sp, la.ev[2 * (b - 1) + 1], 0));
+    for (int k0 = K0; k0 < kend; k0 += TB) {
+      const int kb = (m - k0) < TB ? (m - k0) : TB;
+      potf2_kernel<<<1, 256, 0, sp>>>(w.A, ld, k0, kb, w.pivots, w.info);
       IMB_LAUNCHED();
+      const int t0 = k0 + kb;
+      if (nrows - t0 <= 0) break;
+      trsm_kernel<<<(nrows - t0 + TB - 1) / TB, 64, trsm_smem, sp>>>(w.A, ld, k0, kb, nrows);
+      IMB_LAUNCHED();
+      IMB_TRY(launch_update(w.A, ld, k0, kb, t0, nrows, kend, sp));     // inside the block column
     }
+    IMB_CUDA(cudaEventRecord(la.ev[2 * b], sp));
+    IMB_CUDA(cudaStreamWaitEvent(s, la.ev[2 * b], 0));
+    const int head_end = (m - kend) < OB ? m : kend + OB;
+    IMB_TRY(launch_update(w.A, ld, K0, kend - K0, kend, nrows, head_end, s));      // the next block column
+    IMB_CUDA(cudaEventRecord(la.ev[2 * b + 1], s));
+    IMB_TRY(launch_update(w.A, ld, K0, kend - K0, head_end, nrows, m, s));         // everything to its right
   }
   return IMB_OK;
 }
