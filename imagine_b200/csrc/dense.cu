@@ -1,11 +1,16 @@
-// Stage 3b: the dense covariance route.
-//   S = U^T U / N as a tensor-core GEMM (FP64 DMMA, mma.sync m8n8k4 -- tcgen05 has no f64
-//   kind), fused with the OAS shrinkage and the "+ measurement covariance" epilogue;
-//   blocked right-looking Cholesky (64-wide panels: tile factor in shared memory, triangular
-//   solve of the panel, DMMA trailing update); the right-hand side d rides along as an extra
-//   row, so z = L^-1 d falls out of the factorisation.  Non-symmetric or non-positive-definite
-//   input (the reference is LU throughout and its tests feed np.random.rand matrices,
-//   tests/test_likelihood.py:63-113) takes a partially pivoted LU instead.
+// Stage 3b: the dense covariance route (dense m x m measurement covariances; IMB_ROUTE_AUTO takes the Gram
+// route of gram_batch.cu whenever the measurement covariance is diagonal).
+//   S = U^T U / N as a tensor-core GEMM (FP64 DMMA, mma.sync m8n8k4 -- tcgen05 has no f64 kind), fused
+//   with the OAS shrinkage and the "+ measurement covariance" epilogue;
+//   two-level blocked right-looking Cholesky with lookahead (64-wide panels inside 256-wide block
+//   columns: tile factor, register-resident triangular solve, 128 x 128 DMMA trailing updates fed by a
+//   cp.async ring); the right-hand side d rides along as an extra row, so z = L^-1 d falls out of the
+//   factorisation.  m = 12 288: 33.6 ms for the whole route (cuSOLVER potrf alone on the same matrix:
+//   22 ms; cuBLAS DGEMM on this GPU: 35 TFLOP/s) -- profiles/r02_bench_c2_dense.json.
+//   Non-symmetric or non-positive-definite input (the reference is LU throughout and its tests feed
+//   np.random.rand matrices, tests/test_likelihood.py:63-113) takes a partially pivoted LU instead.
+//   THE LU IS A CORRECTNESS PATH ONLY: unblocked, two launches per column, O(m) launches -- it exists so
+//   that every input the reference accepts gives the reference's answer, not to be fast.
 // Reference arithmetic: oracle/likelihood.py (empirical_mcov / oas_mcov / ensemble_loglike).
 #include <vector>
 #include "common.cuh"
@@ -94,33 +99,33 @@ __global__ void symmetry_kernel(const double* __restrict__ A, int m, int ld, int
 // The tile is reduced in its L D L^T form -- column k keeps t_ik = l_ik l_kk and the update is
 // T[i][j] -= t_ik (t_jk / p_k) -- so that the serial chain of a step is ONE division, no square root and
 // one barrier (sqrt + divide + two barriers per step made this kernel 17 % of the factorisation);
-// L = T / sqrt(p) column by column falls out at the end, in parallel.  256 threads = 4 row groups x 64
-// columns, no index divisions.
-__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ A, int ld, int k0, int kb,
-                                                    double* __restrict__ pivots, int* __restrict__ info) {
-  __shared__ double T[TB][TB + 1];
+// L = T / sqrt(p) column by column falls out at the end, in parallel.
+constexpr int PRG = 16;            // row groups of the tile factor: 1024 threads = 16 row groups x 64 columns
+__global__ void __launch_bounds__(64 * PRG) potf2_kernel(double* __restrict__ A, int ld, int k0, int kb,
+                                                         double* __restrict__ pivots, int* __restrict__ info) {
+  // row TB is a dump row: the update below runs without bounds tests (rows past the tile land there, the
+  // strictly upper triangle is updated along and never read), because every conditional shared-memory
+  // access costs a divergence region of its own.  16 row groups: a thread touches 4 rows per step -- a
+  // step is as long as one warp's instruction chain, not as the block's instruction count.
+  __shared__ double T[TB + 1][TB + 1];
   const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
-  for (int i = ty; i < kb; i += 4)
-    if (tx < kb) T[i][tx] = A[(size_t)(k0 + i) * ld + k0 + tx];
+  for (int i = ty; i <= TB; i += PRG)
+    T[i][tx] = (i < kb && tx < kb) ? A[(size_t)(k0 + i) * ld + k0 + tx] : 0.0;
   __syncthreads();
   for (int k = 0; k + 1 < kb; ++k) {
     if (tx > k && tx < kb) {
       const double u = T[tx][k] / T[k][k];
-      // rows k + 1 + ty + 4 q of column tx, diagonal and below: all loads, then all stores
+      // rows k + 1 + ty + 16 q of column tx: all loads, then all stores
       const int ib = k + 1 + ty;
-      double tik[TB / 4], tv[TB / 4];
+      double tik[TB / PRG], tv[TB / PRG];
 #pragma unroll
-      for (int q = 0; q < TB / 4; ++q) {
-        const int i = ib + 4 * q;
-        const bool ok = i < kb && i >= tx;
-        tik[q] = ok ? T[i][k] : 0.0;
-        tv[q] = ok ? T[i][tx] : 0.0;
+      for (int q = 0; q < TB / PRG; ++q) {
+        const int i = min(ib + PRG * q, TB);
+        tik[q] = T[i][k];
+        tv[q] = T[i][tx];
       }
 #pragma unroll
-      for (int q = 0; q < TB / 4; ++q) {
-        const int i = ib + 4 * q;
-        if (i < kb && i >= tx) T[i][tx] = tv[q] - tik[q] * u;
-      }
+      for (int q = 0; q < TB / PRG; ++q) T[min(ib + PRG * q, TB)][tx] = tv[q] - tik[q] * u;
     }
     __syncthreads();          // column k + 1 (and its pivot) is final
   }
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ A, int 
       pivots[k0 + tx] = p;
       if (!(p > 0.0)) atomicMin(&s_bad, k0 + tx + 1);
     }
-    for (int i = tx + ty; i < kb; i += 4)
+    for (int i = tx + ty; i < kb; i += PRG)
       A[(size_t)(k0 + i) * ld + k0 + tx] = (i == tx) ? lkk : T[i][tx] / lkk;
   }
   __syncthreads();
@@ -282,6 +287,17 @@ __global__ void __launch_bounds__(UTHREADS, 1) chol_update128_kernel(double* __r
   const int nch = K / UK;
   stage(0, 0);
   if (nch > 1) stage(1, 1);
+  // the output tile is read-modify-written by the epilogue with nothing to overlap (one block per SM):
+  // pull it into L2 now.  A warp's 32 x 32 outputs are 32 rows of 256 contiguous bytes.
+  {
+    const int i = i0 + 32 * wi + lane;
+    if (i < nrows) {
+      const double* row = A + (size_t)i * ld + j0 + 32 * wj;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 16));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 31));
+    }
+  }
   for (int c = 0; c < nch; ++c) {
     const int buf = c % UST;
     if (c + 1 < nch) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -563,7 +579,7 @@ static int cholesky(DenseWs& w, int m, cudaStream_t s) {
     if (b > 0) IMB_CUDA(cudaStreamWaitEvent(sp, la.ev[2 * (b - 1) + 1], 0));
     for (int k0 = K0; k0 < kend; k0 += TB) {
       const int kb = (m - k0) < TB ? (m - k0) : TB;
-      potf2_kernel<<<1, 256, 0, sp>>>(w.A, ld, k0, kb, w.pivots, w.info);
+      potf2_kernel<<<1, 64 * PRG, 0, sp>>>(w.A, ld, k0, kb, w.pivots, w.info);
       IMB_LAUNCHED();
       const int t0 = k0 + kb;
       if (nrows - t0 <= 0) break;
