@@ -151,9 +151,11 @@ def test_gram_route_1e8_absolute_vs_extended_precision(eng, N, m):
     assert abs(got - want) <= 1e-8, (got, want, got - want)
 
 
-@pytest.mark.parametrize('N,m', [(16, 768), (8, 1500)])
+@pytest.mark.parametrize('N,m', [(16, 768), (8, 1500), (6, 777), (10, 1290), (4, 2049)])
 def test_dense_vs_gram_vs_reference_algebra(eng, N, m):
-    """Dense DMMA + Cholesky route == Gram route == NumPy dense LU (the reference algebra)."""
+    """Dense DMMA + Cholesky route == Gram route == NumPy dense LU (the reference algebra).  The sizes walk
+    the factorisation's code paths: whole 256-wide block columns (768), a ragged last panel (1500: 28
+    columns, 1290: 10), an odd leading dimension (777, 2049: no 16-byte copies, 64 x 64 update tiles)."""
     rng = np.random.default_rng(m)
     sims = rng.normal(size=(N, m)) * 3 + rng.normal(size=m)
     meas = rng.normal(size=m)
