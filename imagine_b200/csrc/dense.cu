@@ -103,29 +103,21 @@ __global__ void symmetry_kernel(const double* __restrict__ A, int m, int ld, int
 constexpr int PRG = 16;            // row groups of the tile factor: 1024 threads = 16 row groups x 64 columns
 __global__ void __launch_bounds__(64 * PRG) potf2_kernel(double* __restrict__ A, int ld, int k0, int kb,
                                                          double* __restrict__ pivots, int* __restrict__ info) {
-  // row TB is a dump row: the update below runs without bounds tests (rows past the tile land there, the
-  // strictly upper triangle is updated along and never read), because every conditional shared-memory
-  // access costs a divergence region of its own.  16 row groups: a thread touches 4 rows per step -- a
-  // step is as long as one warp's instruction chain, not as the block's instruction count.
-  __shared__ double T[TB + 1][TB + 1];
+  // the strictly upper triangle is updated along and never read; 16 row groups: a thread touches at most
+  // 4 rows per step, with exact loop bounds and constant pointer strides (a step is bound by the
+  // instructions the block issues)
+  __shared__ double T[TB][TB + 1];
   const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
-  for (int i = ty; i <= TB; i += PRG)
+  for (int i = ty; i < TB; i += PRG)
     T[i][tx] = (i < kb && tx < kb) ? A[(size_t)(k0 + i) * ld + k0 + tx] : 0.0;
   __syncthreads();
   for (int k = 0; k + 1 < kb; ++k) {
-    if (tx > k && tx < kb) {
+    if (tx > k && tx < kb && k + 1 + ty < kb) {
       const double u = T[tx][k] / T[k][k];
-      // rows k + 1 + ty + 16 q of column tx: all loads, then all stores
-      const int ib = k + 1 + ty;
-      double tik[TB / PRG], tv[TB / PRG];
-#pragma unroll
-      for (int q = 0; q < TB / PRG; ++q) {
-        const int i = min(ib + PRG * q, TB);
-        tik[q] = T[i][k];
-        tv[q] = T[i][tx];
-      }
-#pragma unroll
-      for (int q = 0; q < TB / PRG; ++q) T[min(ib + PRG * q, TB)][tx] = tv[q] - tik[q] * u;
+      // rows k + 1 + ty, + 16, ...: exact bounds, pointers stepped by a constant
+      const double* pk = &T[k + 1 + ty][k];
+      double* pt = &T[k + 1 + ty][tx];
+      for (int i = k + 1 + ty; i < kb; i += PRG, pk += PRG * (TB + 1), pt += PRG * (TB + 1)) *pt = fma(-*pk, u, *pt);
     }
     __syncthreads();          // column k + 1 (and its pivot) is final
   }

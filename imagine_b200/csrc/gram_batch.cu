@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256) bg_reduce_kernel(const __grid_constant__ 
 }
 
 // OAS shrinkage (covariance_estimator.py:222-234) from tr G and ||G||_F; m = TOTAL pixel count
-__global__ void __launch_bounds__(256) bg_oas_kernel(const __grid_constant__ BatchWs ws, int N,
+__global__ void __launch_bounds__(1024) bg_oas_kernel(const __grid_constant__ BatchWs ws, int N,
                                                      double m_total, int estimator) {
   __shared__ double red[32];
   const KeyWs& kw = ws.k[blockIdx.x];
@@ -504,13 +504,12 @@ __global__ void __launch_bounds__(256) bg_finish_kernel(const __grid_constant__ 
 }
 
 // The same for N <= 64 on 1024 threads = 16 row groups x 64 columns: a thread touches at most 5 rows per
-// column step, every shared-memory access is unconditional (rows past the right-hand side land in a
-// dump row, the strictly upper triangle is updated along and never read -- a conditional shared access
-// costs a divergence region each), and the pivot enters as u_j = t_jk / p_k.  61 -> about 20 us at N = 64.
+// column step, the row loop has exact bounds and constant pointer strides (the step is bound by the
+// instructions the block issues: index arithmetic and clamps cost more than the update itself), the
+// strictly upper triangle is updated along and never read, and the pivot enters as u_j = t_jk / p_k.
 constexpr int FRG = 16;
 __global__ void __launch_bounds__(64 * FRG) bg_finish64_kernel(const __grid_constant__ BatchWs ws, int N) {
-  constexpr int DUMP = 65;
-  __shared__ double T[DUMP + 1][65];
+  __shared__ double T[65][65];
   __shared__ int bad;
   __shared__ double red[32];
   const KeyWs& kw = ws.k[blockIdx.x];
@@ -519,7 +518,7 @@ __global__ void __launch_bounds__(64 * FRG) bg_finish64_kernel(const __grid_cons
   const double* tail = kw.P2 + (size_t)N * N;
   if (tid == 0) bad = 0x7fffffff;
   const double c = sc->c;
-  for (int i = ty; i <= DUMP; i += FRG) {
+  for (int i = ty; i <= 64; i += FRG) {
     double v = 0.0;
     if (tx < N) {
       if (i < N) v = (i == tx ? 1.0 : 0.0) + c * kw.P2[(size_t)i * N + tx];
@@ -529,21 +528,12 @@ __global__ void __launch_bounds__(64 * FRG) bg_finish64_kernel(const __grid_cons
   }
   __syncthreads();
   for (int k = 0; k + 1 < N; ++k) {
-    if (tx > k && tx < N) {
+    if (tx > k && tx < N && k + 1 + ty <= N) {
       const double u = T[tx][k] * (1.0 / T[k][k]);
-      const int ib = k + 1 + ty;                      // rows k + 1 .. N (row N = rhs)
-      double tik[5], tv[5];
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const int i = min(ib + FRG * q, DUMP);
-        tik[q] = T[i][k];
-        tv[q] = T[i][tx];
-      }
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const int i = ib + FRG * q;
-        T[i > N ? DUMP : i][tx] = tv[q] - tik[q] * u;
-      }
+      // rows k + 1 + ty, + 16, ... up to N (row N = rhs): exact bounds, pointers stepped by a constant
+      const double* pk = &T[k + 1 + ty][k];
+      double* pt = &T[k + 1 + ty][tx];
+      for (int i = k + 1 + ty; i <= N; i += FRG, pk += FRG * 65, pt += FRG * 65) *pt = fma(-*pk, u, *pt);
     }
     __syncthreads();
   }
@@ -572,6 +562,135 @@ __global__ void __launch_bounds__(64 * FRG) bg_finish64_kernel(const __grid_cons
   }
 }
 
+// 64 < N <= ~370 (C4: N = 256): T = (N + 1) x N does not fit in shared memory, a 64-column PANEL of it
+// does.  One block of 1024 threads per key walks the panels left to right: the panel (all rows from its
+// diagonal block down to the right-hand-side row) is factored in shared memory with the same branch-free
+// column step as above, then the columns to its right are updated in place in global memory (L2-resident,
+// 0.5 MB per key) with the panel and its pivot-scaled transpose as shared-memory operands.  The kernel
+// it replaces for these sizes kept T in global memory for every one of the N column steps: 2.4 ms at
+// N = 256, 56 % of the C4 likelihood stage.
+constexpr int FPW = 64;
+__host__ __device__ inline size_t finish_panel_smem(int N) {
+  return sizeof(double) * ((size_t)(N + 2) * 65 + (size_t)FPW * 65 + 2 * (size_t)N + FPW);
+}
+__global__ void __launch_bounds__(1024) bg_finish_panel_kernel(const __grid_constant__ BatchWs ws, int N, int ldt) {
+  extern __shared__ double fsm[];
+  double (*P)[65] = reinterpret_cast<double (*)[65]>(fsm);
+  double (*Us)[65] = reinterpret_cast<double (*)[65]>(fsm + (size_t)(N + 2) * 65);
+  double* piv = fsm + (size_t)(N + 2) * 65 + (size_t)FPW * 65;
+  double* zr = piv + N;
+  double* pinv = zr + N;
+  __shared__ int bad;
+  __shared__ double red[32];
+  const KeyWs& kw = ws.k[blockIdx.x];
+  LikeScalars* sc = kw.sc;
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+  double* T = kw.partial;                      // free again: global scratch, (N + 1) x ldt
+  const double* tail = kw.P2 + (size_t)N * N;
+  if (tid == 0) bad = 0x7fffffff;
+  const double c = sc->c;
+  for (int i = ty; i < N; i += FRG)
+    for (int j = tx; j < N; j += 64) T[(size_t)i * ldt + j] = (i == j ? 1.0 : 0.0) + c * kw.P2[(size_t)i * N + j];
+  for (int r = tid; r < N; r += 1024) T[(size_t)N * ldt + r] = tail[r];
+  __syncthreads();
+  for (int p0 = 0; p0 < N; p0 += FPW) {
+    const int pw = min(FPW, N - p0);
+    const int R = N + 1 - p0;                  // panel rows: p0 .. N (the rhs)
+    for (int r = ty; r < R; r += FRG) P[r][tx] = tx < pw ? T[(size_t)(p0 + r) * ldt + p0 + tx] : 0.0;
+    __syncthreads();
+    for (int k = 0; k < pw; ++k) {
+      if (tx > k && tx < pw && k + 1 + ty < R) {
+        const double u = P[tx][k] * (1.0 / P[k][k]);
+        const double* pk = &P[k + 1 + ty][k];
+        double* pt = &P[k + 1 + ty][tx];
+        for (int i = k + 1 + ty; i < R; i += FRG, pk += FRG * 65, pt += FRG * 65) *pt = fma(-*pk, u, *pt);
+      }
+      __syncthreads();
+    }
+    if (tid < pw) {
+      const double pv = P[tid][tid];
+      piv[p0 + tid] = pv;
+      zr[p0 + tid] = P[R - 1][tid];
+      pinv[tid] = 1.0 / pv;
+    }
+    __syncthreads();
+    for (int jb = p0 + FPW; jb < N; jb += FPW) {
+      const int j = jb + tx;
+#pragma unroll
+      for (int kk = 0; kk < FPW / FRG; ++kk) {
+        const int k = ty * (FPW / FRG) + kk;
+        Us[tx][k] = (j < N && k < pw) ? P[j - p0][k] * pinv[k] : 0.0;
+      }
+      __syncthreads();
+      for (int i = jb + ty; i <= N; i += FRG) {
+        const double* pr = P[i - p0];
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll 16
+        for (int k = 0; k < FPW; k += 2) {
+          a0 = fma(pr[k], Us[tx][k], a0);
+          a1 = fma(pr[k + 1], Us[tx][k + 1], a1);
+        }
+        if (j < N && j <= i) T[(size_t)i * ldt + j] -= a0 + a1;
+      }
+      __syncthreads();
+    }
+  }
+  double ld = 0.0, zz = 0.0;
+  int first_bad = 0x7fffffff;
+  if (tid < N) {
+    const double pv = piv[tid], z = zr[tid];
+    if (!(pv > 0.0)) first_bad = tid + 1;
+    ld = log(pv);
+    zz = z * z / pv;
+  }
+  ld = block_sum(ld, red);
+  zz = block_sum(zz, red);
+  atomicMin(&bad, first_bad);
+  __syncthreads();
+  if (tid == 0) {
+    const double s_quad = tail[N], s_logdet = tail[N + 1];
+    const double quad = s_quad - c * zz;
+    const double logdet = s_logdet + ld;
+    const double sign = (((long long)tail[N + 3]) & 1) ? -1.0 : 1.0;
+    sc->s_quad = s_quad; sc->s_logdet = s_logdet;
+    sc->quad = quad; sc->logdet = logdet; sc->sign = sign;
+    sc->nonpos = (int)tail[N + 2];
+    sc->info = bad == 0x7fffffff ? 0 : bad;
+    sc->loglike = -0.5 * (quad + sign * logdet);
+  }
+}
+
+// the Cholesky finish for c.N: N <= 64, a panel kernel while a panel fits in shared memory, else global
+static int launch_finish(const BatchWs& ws, int K, int N, cudaStream_t s) {
+  if (N <= 64) {
+    bg_finish64_kernel<<<K, 64 * FRG, 0, s>>>(ws, N);
+    IMB_LAUNCHED();
+    return IMB_OK;
+  }
+  const int ldt = N + 1;
+  const size_t psm = finish_panel_smem(N);
+  if (psm <= 220 * 1024 && N <= 1024) {
+    static size_t attr_panel = 0;
+    if (psm > attr_panel) {
+      IMB_CUDA(cudaFuncSetAttribute(bg_finish_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+      attr_panel = psm;
+    }
+    bg_finish_panel_kernel<<<K, 1024, psm, s>>>(ws, N, ldt);
+    IMB_LAUNCHED();
+    return IMB_OK;
+  }
+  const size_t smem = sizeof(double) * (size_t)(N + 1) * ldt;
+  const int use_smem = smem <= 200 * 1024;
+  static size_t attr_bytes = 0;
+  if (use_smem && smem > 48 * 1024 && smem > attr_bytes) {
+    IMB_CUDA(cudaFuncSetAttribute(bg_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bytes = smem;
+  }
+  bg_finish_kernel<<<K, 256, use_smem ? smem : 0, s>>>(ws, N, use_smem, ldt);
+  IMB_LAUNCHED();
+  return IMB_OK;
+}
+
 // ---- host ---------------------------------------------------------------------------------
 struct BatchCtx {
   int K, N, m, slices, dparts, nn;
@@ -596,7 +715,7 @@ static int make_ctx(BatchCtx* c, int K, const double* const* sims, int N, int m,
   c->use64 = N <= 64 && m % 2 == 0 && L.bstride % 2 == 0 && L.rstride % 2 == 0;
   for (int k = 0; c->use64 && sims && k < K; ++k)
     if (reinterpret_cast<uintptr_t>(sims[k]) % 16 != 0) c->use64 = false;
-  c->cols = !c->use64 ? GCOLS : (m >= 32768 ? 1024 : (m >= 8192 ? 512 : GCOLS));
+  c->cols = !c->use64 ? (m >= 8192 ? 512 : GCOLS) : (m >= 32768 ? 1024 : (m >= 8192 ? 512 : GCOLS));
   c->slices = (m + c->cols - 1) / c->cols;
   const size_t max_slices = (m + GCOLS - 1) / GCOLS;     // sizing is the same for both kernels
   const size_t nn = c->nn, p2 = nn + N + 4;
@@ -651,7 +770,7 @@ static int phase1(const BatchCtx& c, cudaStream_t s) {
     IMB_LAUNCHED();
     return IMB_OK;
   }
-  bg_gram_kernel<false><<<dim3(c.slices, nb * nb, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, GCOLS, c.L);
+  bg_gram_kernel<false><<<dim3(c.slices, nb * nb, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, c.cols, c.L);
   IMB_LAUNCHED();
   bg_reduce_kernel<<<dim3((c.nn + 255) / 256, c.K), 256, 0, s>>>(c.ws, c.nn, c.slices, 0, c.N);
   IMB_LAUNCHED();
@@ -660,7 +779,7 @@ static int phase1(const BatchCtx& c, cudaStream_t s) {
 
 static int phase2(const BatchCtx& c, double m_total, int estimator, cudaStream_t s) {
   const int nb = (c.N + TB - 1) / TB;
-  bg_oas_kernel<<<c.K, 256, 0, s>>>(c.ws, c.N, m_total, estimator);
+  bg_oas_kernel<<<c.K, c.N > 64 ? 1024 : 256, 0, s>>>(c.ws, c.N, m_total, estimator);
   IMB_LAUNCHED();
   bg_dvec_kernel<<<dim3(c.dparts, c.K), 256, 0, s>>>(c.p, c.ws, c.m);
   IMB_LAUNCHED();
@@ -671,11 +790,11 @@ static int phase2(const BatchCtx& c, double m_total, int estimator, cudaStream_t
     bg_reduce64_kernel<<<dim3((c.nn + 255) / 256, c.K), 256, 0, s>>>(c.ws, c.nn, c.slices, 1, c.N);
     IMB_LAUNCHED();
   } else {
-    bg_gram_kernel<true><<<dim3(c.slices, nb * nb, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, GCOLS, c.L);
+    bg_gram_kernel<true><<<dim3(c.slices, nb * nb, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, c.cols, c.L);
     IMB_LAUNCHED();
     bg_reduce_kernel<<<dim3((c.nn + 255) / 256, c.K), 256, 0, s>>>(c.ws, c.nn, c.slices, 1, c.N);
     IMB_LAUNCHED();
-    bg_wdot_kernel<<<dim3(c.slices, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, GCOLS, c.L);
+    bg_wdot_kernel<<<dim3(c.slices, c.K), 256, 0, s>>>(c.p, c.ws, c.N, c.m, c.cols, c.L);
     IMB_LAUNCHED();
   }
   bg_pack2_kernel<<<c.K, 256, 0, s>>>(c.ws, c.N, c.slices, c.dparts);
@@ -684,17 +803,7 @@ static int phase2(const BatchCtx& c, double m_total, int estimator, cudaStream_t
 }
 
 static int phase3(const BatchCtx& c, LikeScalars* h_out, cudaStream_t s) {
-  const int ldt = c.N + 1;
-  const size_t smem = sizeof(double) * (size_t)(c.N + 1) * ldt;
-  const int use_smem = smem <= 200 * 1024;
-  static size_t attr_bytes = 0;
-  if (use_smem && smem > 48 * 1024 && smem > attr_bytes) {
-    IMB_CUDA(cudaFuncSetAttribute(bg_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_bytes = smem;
-  }
-  if (c.N <= 64) bg_finish64_kernel<<<c.K, 64 * FRG, 0, s>>>(c.ws, c.N);
-  else bg_finish_kernel<<<c.K, 256, use_smem ? smem : 0, s>>>(c.ws, c.N, use_smem, ldt);
-  IMB_LAUNCHED();
+  IMB_TRY(launch_finish(c.ws, c.K, c.N, s));
   LikeScalars* h = static_cast<LikeScalars*>(state().pinned);
   IMB_CUDA(cudaMemcpyAsync(h, c.sc0, sizeof(LikeScalars) * c.K, cudaMemcpyDeviceToHost, s));
   IMB_CUDA(cudaStreamSynchronize(s));
@@ -713,17 +822,7 @@ __global__ void bg_export_kernel(const __grid_constant__ BatchWs ws, int K, doub
 }
 
 static int finish_async(const BatchCtx& c, double* out_device, int32_t* flag_device, cudaStream_t s) {
-  const int ldt = c.N + 1;
-  const size_t smem = sizeof(double) * (size_t)(c.N + 1) * ldt;
-  const int use_smem = smem <= 200 * 1024;
-  static size_t attr_bytes = 0;
-  if (use_smem && smem > 48 * 1024 && smem > attr_bytes) {
-    IMB_CUDA(cudaFuncSetAttribute(bg_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_bytes = smem;
-  }
-  if (c.N <= 64) bg_finish64_kernel<<<c.K, 64 * FRG, 0, s>>>(c.ws, c.N);
-  else bg_finish_kernel<<<c.K, 256, use_smem ? smem : 0, s>>>(c.ws, c.N, use_smem, ldt);
-  IMB_LAUNCHED();
+  IMB_TRY(launch_finish(c.ws, c.K, c.N, s));
   bg_export_kernel<<<1, 32, 0, s>>>(c.ws, c.K, out_device, flag_device);
   IMB_LAUNCHED();
   return IMB_OK;

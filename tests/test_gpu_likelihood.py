@@ -121,9 +121,12 @@ def test_single_row_ensemble_zero_covariance(eng):
         assert np.all(cov.cpu().numpy() == 0.0)
 
 
-@pytest.mark.parametrize('N,m', [(16, 3072), (64, 12288), (3, 1000), (200, 517), (64, 49152)])
+@pytest.mark.parametrize('N,m', [(16, 3072), (64, 12288), (3, 1000), (200, 517), (64, 49152), (65, 2048), (130, 4096),
+                                 (256, 24576), (400, 1024)])
 def test_gram_route_at_scale_vs_oracle_gram(eng, N, m):
-    """Sizes where the dense oracle is too slow: compare with the O(mN^2) NumPy restatement."""
+    """Sizes where the dense oracle is too slow: compare with the O(mN^2) NumPy restatement.  The ensemble sizes
+    walk the three Cholesky finishes of the Gram route: N <= 64 in shared memory, 64 < N <= ~370 panel by
+    panel (65: one column in the second panel; 256 = the C4 shard), above that in global memory (400)."""
     rng = np.random.default_rng(N * m)
     base = 30 * rng.normal(size=m)
     sims = base + 8 * rng.normal(size=(N, m))
