@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # IMB_LIB_PATH: A/B runs of tuning builds (tools/build_variant.sh); the product is the in-tree default
 LIB_PATH = os.environ.get('IMB_LIB_PATH') or os.path.join(HERE, 'libimagine_b200.so')
 
-IMB_OK, IMB_EINVAL, IMB_ECUDA, IMB_ENOMEM, IMB_ENOTINIT, IMB_EBOUNDS, IMB_ESINGULAR, IMB_EUNSUPPORTED = range(8)
+IMB_OK, IMB_EINVAL, IMB_ECUDA, IMB_ENOMEM, IMB_ENOTINIT, IMB_EBOUNDS, IMB_ESINGULAR, IMB_EUNSUPPORTED, IMB_ESTATE = range(9)
 
 # field kinds (include/imagine_b200.h)
 (FIELD_CONST_B, FIELD_GAUSS_B, FIELD_CONST_NE, FIELD_EXP_NE, FIELD_COS_NE, FIELD_RANDOM_NE,

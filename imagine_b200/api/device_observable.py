@@ -99,7 +99,8 @@ class ShardedDeviceObservable(Observable):
     a collective, so every rank must ask for it.
     """
 
-    def __init__(self, recv, index, n_real, m, rank, world, group=None, unit=None, coords=None, otype=None):
+    def __init__(self, recv, index, n_real, m, rank, world, group=None, unit=None, coords=None, otype=None,
+                 still_valid=None):
         self._dtype = 'simulated'
         self.otype, self.unit, self.coords = otype, unit, coords
         self._rw_flag = False
@@ -108,6 +109,16 @@ class ShardedDeviceObservable(Observable):
         self.rank, self.world, self.group = int(rank), int(world), group
         self._full = None
         self._host = None
+        # exchange='peer': `recv` is the simulator's persistent NVLink buffer, which the NEXT simulator call
+        # (and the other ranks' kernels) overwrite; `still_valid()` turns a late read into an error
+        self._still_valid = still_valid
+
+    def _check_fresh(self):
+        if self._still_valid is not None and not self._still_valid():
+            raise RuntimeError('this Simulations object belongs to an earlier evaluation: with exchange="peer" '
+                               'the maps live in the simulator\'s NVLink receive buffer, which the next '
+                               'simulator call overwrites; read `.tensor` / `.data` (or evaluate the '
+                               'likelihood) before simulating again, or use exchange="alltoall"')
 
     # layout of the rows of this key inside `recv` (imb_gram_phase*): rows_per_block, strides
     @property
@@ -124,6 +135,7 @@ class ShardedDeviceObservable(Observable):
 
     @property
     def base(self):
+        self._check_fresh()
         return self.recv[0, self.index]
 
     @property
@@ -133,6 +145,7 @@ class ShardedDeviceObservable(Observable):
     @property
     def local_block(self):
         """[N, m_local]: every realisation of this rank's pixels (copy)."""
+        self._check_fresh()
         return self.recv[:, self.index].reshape(self.n_real, self.m_local)
 
     @property

@@ -388,8 +388,11 @@ class B200Simulator(Simulator):
                 self.exchange_note = 'all-to-all: symmetric memory unavailable (%s: %s)' % (type(exc).__name__, exc)
                 if self.rank == 0:
                     log.warning('B200Simulator exchange fallback -- %s', self.exchange_note)
+        still_valid = None
         if self._peer is not None and tuple(self._peer.recv.shape) == shape:
             recv = self._peer.recv
+            self._peer_generation = generation = getattr(self, '_peer_generation', 0) + 1
+            still_valid = lambda: self._peer_generation == generation
             views = {key: recv[self.rank, k] for k, key in enumerate(self.observables)}
             self._integrate(dg, dev_fields, n_local, sharded=(views, (mp, 0, self._peer.peer_delta)))
             self._peer.barrier()
@@ -408,7 +411,8 @@ class B200Simulator(Simulator):
             unit = self.output_units.get(key) or self._units(key)
             sims.append(name=key,
                         data=ShardedDeviceObservable(recv, k, N, m, self.rank, self.world, self.group, unit,
-                                                     self.output_coords[key], self.output_type[key]),
+                                                     self.output_coords[key], self.output_type[key],
+                                                     still_valid=still_valid),
                         coords=self.output_coords[key], otype=self.output_type[key])
         return sims
 

@@ -114,6 +114,8 @@ const char* imb_strerror(int code) {
     case IMB_EBOUNDS: return "one of the requested points is out of the grid bounds";
     case IMB_ESINGULAR: return "singular matrix";
     case IMB_EUNSUPPORTED: return "unsupported configuration";
+    case IMB_ESTATE:
+      return "the scratch workspace was used by another call between the phases of a sharded evaluation";
     default: return "unknown error code";
   }
 }

@@ -24,6 +24,9 @@ struct State {
   void* pinned = nullptr;      // small pinned host buffer for scalar read-back
   size_t pinned_bytes = 0;
   long long launches = 0;
+  // every call that carves the scratch workspace bumps ws_epoch; the phased (sharded) Gram route records the
+  // epoch of its phase 1 and refuses to continue if anything else used the workspace in between
+  unsigned long long ws_epoch = 0, phase_epoch = 0;
   char cuda_err[256] = {0};
 };
 State& state();

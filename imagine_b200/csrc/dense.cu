@@ -476,6 +476,7 @@ static int carve_dense(int N, int m, DenseWs* w) {
   const size_t need = 256 * 16 + sizeof(LikeScalars) + 64 +
                       sizeof(double) * ((size_t)5 * m + (size_t)(slices + 1) * N * N + a_elems);
   IMB_TRY(ensure_workspace(need));
+  ++state().ws_epoch;
   Carver c(state().ws);
   w->sc = c.take<LikeScalars>(1);
   w->info = c.take<int>(4);
@@ -702,6 +703,7 @@ extern "C" int imb_mcov(const double* sims, int N, int m, int estimator, double*
   const int slices = gram_slices(m);
   IMB_TRY(ensure_workspace(256 * 8 + sizeof(LikeScalars) +
                            sizeof(double) * ((size_t)m + (size_t)(slices + 1) * N * N)));
+  ++state().ws_epoch;
   Carver c(state().ws);
   LikeScalars* sc = c.take<LikeScalars>(1);
   double* xvar = c.take<double>(m);

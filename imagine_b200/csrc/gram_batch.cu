@@ -705,8 +705,11 @@ struct BatchCtx {
 // Deterministic carving: the three phases of one evaluation see the same pointers as long as no
 // other library call grows the workspace in between.  G / P2 may be caller-owned (contiguous
 // [K, nn] and [K, nn + N + 4]) so that torch.distributed can all-reduce them.
+// phase: 0 = a self-contained evaluation, 1 = first phase of a sharded one (both claim the workspace),
+// 2 / 3 = later phases (the workspace must still be the one phase 1 claimed: IMB_ESTATE otherwise)
 static int make_ctx(BatchCtx* c, int K, const double* const* sims, int N, int m, RowLayout L,
-                    const double* const* meas, const double* const* var, double* G_ext, double* P2_ext) {
+                    const double* const* meas, const double* const* var, double* G_ext, double* P2_ext,
+                    int phase = 0) {
   if (K < 1 || K > KMAX) return IMB_EINVAL;
   c->K = K; c->N = N; c->m = m; c->L = L;
   c->nn = N * N;
@@ -724,7 +727,10 @@ static int make_ctx(BatchCtx* c, int K, const double* const* sims, int N, int m,
   const size_t per_key = 256 * 12 + sizeof(LikeScalars) +
                          sizeof(double) * ((size_t)3 * m + partial_elems + nn + p2 + max_slices * N +
                                            4 * (size_t)c->dparts);
+  if (phase >= 2 && (state().phase_epoch != state().ws_epoch || per_key * K + 512 > state().ws_bytes))
+    return IMB_ESTATE;
   IMB_TRY(ensure_workspace(per_key * K + 512));
+  if (phase < 2) state().phase_epoch = ++state().ws_epoch;
   Carver cv(state().ws);
   c->sc0 = cv.take<LikeScalars>(K);
   double* G_int = cv.take<double>((size_t)K * nn);
@@ -907,7 +913,7 @@ int imb_gram_phase3_async(int K, int N, int m_local, double* G, double* P2, doub
   if (K < 1 || K > KMAX || N < 1 || m_local < 1 || !G || !P2 || !out_device) return IMB_EINVAL;
   const RowLayout L{N, 0, (long long)m_local};
   BatchCtx c;
-  IMB_TRY(make_ctx(&c, K, nullptr, N, m_local, L, nullptr, nullptr, G, P2));
+  IMB_TRY(make_ctx(&c, K, nullptr, N, m_local, L, nullptr, nullptr, G, P2, 3));
   return finish_async(c, out_device, flag_device, (cudaStream_t)stream);
 }
 
@@ -925,7 +931,7 @@ int imb_gram_phase1(int K, const double* const* sims, int N, int m_local, int ro
   if (!sharded_args_ok(K, sims, N, m_local, rows_per_block) || !meas || !G) return IMB_EINVAL;
   const RowLayout L{rows_per_block, (long long)block_stride, (long long)row_stride};
   BatchCtx c;
-  IMB_TRY(make_ctx(&c, K, sims, N, m_local, L, meas, nullptr, G, nullptr));
+  IMB_TRY(make_ctx(&c, K, sims, N, m_local, L, meas, nullptr, G, nullptr, 1));
   return phase1(c, (cudaStream_t)stream);
 }
 
@@ -939,7 +945,7 @@ int imb_gram_phase2(int K, const double* const* sims, int N, int m_local, int ro
   if (estimator != IMB_EST_EMPIRICAL && estimator != IMB_EST_OAS) return IMB_EINVAL;
   const RowLayout L{rows_per_block, (long long)block_stride, (long long)row_stride};
   BatchCtx c;
-  IMB_TRY(make_ctx(&c, K, sims, N, m_local, L, meas, var, G, P2));
+  IMB_TRY(make_ctx(&c, K, sims, N, m_local, L, meas, var, G, P2, 2));
   return phase2(c, (double)m_total, estimator, (cudaStream_t)stream);
 }
 
@@ -949,7 +955,7 @@ int imb_gram_phase3(int K, int N, int m_local, double* G, double* P2, double* ou
   if (K < 1 || K > KMAX || N < 1 || m_local < 1 || !G || !P2 || !out_loglike) return IMB_EINVAL;
   const RowLayout L{N, 0, (long long)m_local};
   BatchCtx c;
-  IMB_TRY(make_ctx(&c, K, nullptr, N, m_local, L, nullptr, nullptr, G, P2));
+  IMB_TRY(make_ctx(&c, K, nullptr, N, m_local, L, nullptr, nullptr, G, P2, 3));
   LikeScalars h[KMAX];
   IMB_TRY(phase3(c, h, (cudaStream_t)stream));
   unpack(h, K, out_loglike, out_info, nullptr);

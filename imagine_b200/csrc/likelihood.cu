@@ -265,6 +265,7 @@ int loglike_diag(const double* sims, int N, int m, const double* meas, const dou
   const int nparts = grid_blocks(m, 256, 2);
   IMB_TRY(ensure_workspace(256 * 8 + sizeof(double) * ((size_t)3 * m + 4 * (size_t)nparts) +
                            sizeof(LikeScalars)));
+  ++state().ws_epoch;
   Carver c(state().ws);
   LikeScalars* sc = c.take<LikeScalars>(1);
   double* mean = c.take<double>(m);

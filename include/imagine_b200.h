@@ -38,7 +38,9 @@ enum {
   IMB_ENOTINIT = 4,      /* imb_init not called                                           */
   IMB_EBOUNDS = 5,       /* tabulated point outside the grid hull (ValueError)            */
   IMB_ESINGULAR = 6,     /* exactly singular matrix in LU (numpy.linalg.LinAlgError)      */
-  IMB_EUNSUPPORTED = 7   /* combination not implemented                                   */
+  IMB_EUNSUPPORTED = 7,  /* combination not implemented                                   */
+  IMB_ESTATE = 8         /* imb_gram_phase2/3 after another call used the library's scratch workspace:
+                            the phases of one sharded evaluation must follow each other on one stream   */
 };
 
 /* ---- geometry: UniformGrid, cartesian (fields/grid.py:189-275) --------------------- */

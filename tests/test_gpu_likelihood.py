@@ -290,6 +290,33 @@ def test_phased_gram_route_over_pixel_shards(eng, N, m, K, P):
             assert abs(got[k] - want[k]) <= 1e-9 * max(1.0, abs(want[k])), (est, k, got[k], want[k])
 
 
+def test_phased_route_refuses_a_workspace_somebody_else_used(eng):
+    """The phases of one sharded evaluation share the library's scratch (means, weights, scalars): a call that
+    carves the workspace between phase 1 and phase 2 must turn phase 2 into an error (IMB_ESTATE), not into
+    a wrong number."""
+    import torch
+    from imagine_b200 import _lib
+    rng = np.random.default_rng(3)
+    N, m, K = 8, 256, 2
+    sims = [_dev(rng.normal(size=(N, m))) for _ in range(K)]
+    meas = [_dev(rng.normal(size=m)) for _ in range(K)]
+    var = [_dev(rng.uniform(0.5, 1.5, size=m)) for _ in range(K)]
+    layout = (N, 0, m)
+    G = torch.zeros((K, N, N), dtype=torch.float64, device='cuda')
+    P2 = torch.zeros((K, N * N + N + 4), dtype=torch.float64, device='cuda')
+    eng.gram_phase1(sims, N, m, layout, meas, G)
+    eng.gram_phase2(sims, N, m, layout, meas, var, m, G, P2)          # undisturbed: fine
+    want = eng.gram_phase3(K, N, m, G, P2)
+    eng.gram_phase1(sims, N, m, layout, meas, G)
+    eng.loglike_ensemble_diagonal(sims[0], meas[0], var[0])            # somebody else takes the workspace
+    with pytest.raises(_lib.ImbError) as err:
+        eng.gram_phase2(sims, N, m, layout, meas, var, m, G, P2)
+    assert err.value.code == _lib.IMB_ESTATE
+    eng.gram_phase1(sims, N, m, layout, meas, G)                       # starting over works
+    eng.gram_phase2(sims, N, m, layout, meas, var, m, G, P2)
+    assert eng.gram_phase3(K, N, m, G, P2) == want
+
+
 def test_edge_shapes(eng):
     """Smallest / ragged inputs: one pixel, one realisation, empty masks, N >> m."""
     import torch

@@ -34,7 +34,7 @@ def _setup(rank, world, exchange, N=N):
     return ev, seeds, meas, var
 
 
-def _plugin_value(rank, world):
+def _plugin_value(rank, world, exchange='auto', twice=False):
     import imagine_b200.api as api
     u = api.units
     m = 12 * NSIDE ** 2
@@ -46,7 +46,7 @@ def _plugin_value(rank, world):
     for q in QUANT:
         M.append(name=keys[q], data=meas[q].cpu().numpy().reshape(1, m), cov_data=var[q].cpu().numpy(),
                  otype='HEALPix')
-    sim = api.B200Simulator(M, radial_step=0.25, rank=rank, world=world)
+    sim = api.B200Simulator(M, radial_step=0.25, rank=rank, world=world, exchange=exchange)
     lik = api.B200EnsembleLikelihood(M)
     fields = [api.ExponentialThermalElectrons(grid, parameters={'central_density': 0.01 * u.cm ** -3,
                                                                 'scale_radius': 3 * u.kpc,
@@ -58,6 +58,13 @@ def _plugin_value(rank, world):
               api.AnalyticCosmicRayElectrons(grid, parameters={'j0': 0.0217, 'r0': 5 * u.kpc, 'z0': 1 * u.kpc,
                                                                'r_sun': 8.3 * u.kpc}, ensemble_size=N)]
     sims = sim(fields)
+    if twice:                     # exchange='peer': the first Simulations aliases a buffer the second call reuses
+        first, sims = sims, sim(fields)
+        try:
+            lik(first)
+            return 'no error', sims
+        except RuntimeError as exc:
+            return ('stale' if 'earlier evaluation' in str(exc) else repr(exc)), sims
     return lik(sims), sims
 
 
@@ -109,6 +116,8 @@ def _worker(rank, world, port, queue):
     key = ('sync', 23.0, NSIDE, 'Q')
     out['plugin_sharded'] = type(sims[key]).__name__
     out['plugin_full_Q'] = sims[key].data           # collective all-gather on every rank
+    out['plugin_peer'] = _plugin_value(rank, world, exchange='peer')[0]
+    out['plugin_peer_stale'] = _plugin_value(rank, world, exchange='peer', twice=True)[0]
     queue.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -151,6 +160,8 @@ def test_two_gpu_paths_match_single_gpu():
         for mode in ('tiny_peer', 'tiny_allgather'):
             assert abs(out[mode] - want_tiny) <= 1e-9 * max(1.0, abs(want_tiny)), mode
         assert abs(out['plugin'] - want_plugin) <= 1e-9 * max(1.0, abs(want_plugin))
+        assert out['plugin_peer'] == out['plugin']          # same kernels, other transport
+        assert out['plugin_peer_stale'] == 'stale'          # a Simulations kept past the next call is refused
         q1 = sims1[('sync', 23.0, NSIDE, 'Q')].data
         assert np.allclose(out['plugin_full_Q'], q1, rtol=1e-9, atol=1e-12 * np.abs(q1).max())
     assert results[0][1]['alltoall'] == results[1][1]['alltoall']         # replicated scalar
