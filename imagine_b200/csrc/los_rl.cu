@@ -42,6 +42,9 @@
 // built once per grid / observer / direction set, 80 B per sample, read back by phase A instead of being
 // recomputed): bit-identical maps, but 2.23 vs 2.16 ms at 64 realisations, 1.10 vs 1.14 at 32, 0.56 vs 0.55
 // at 8 -- phase A is bound by its block-wide barrier and the (n_e, CRE) gathers, not by the arithmetic.
+// RL = 8 / 16 (several segments per warp, L1 data pipe at 80 %): the step slot carrying the three cell
+// fractions and each lane rebuilding the eight weights itself (24 instead of 64 bytes of shared reads per
+// step, 21 more FP64 instructions): 0.494 vs 0.496 ms at RL 8, 0.735 vs 0.712 at RL 16 -- dropped.
 // Numeric definition: oracle/los.py.
 #include <cstdlib>
 #include <type_traits>
