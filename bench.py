@@ -306,6 +306,29 @@ def main():
                      'value': n_flush * args.points / (float(pip_ms[0]) * 1e-3), 'unit': 'evals/s',
                      'loglike': many[-1]}
 
+    # ---- several parameter points per LAUNCH: the lanes of one ray march are (point,
+    # realisation) pairs; applies on the pixel-sharded path with <= 16 local realisations
+    batched = None
+    if args.points > 1 and ev.batch_capacity([(descs, seeds)] * 2) >= 2:
+        pts = [(descs, seeds)] * args.points
+        ev.evaluate_batch(pts, meas_d, var_d)
+        barrier()
+        n_flush = max(1, args.steps // args.points)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(n_flush):
+            bvals = ev.evaluate_batch(pts, meas_d, var_d)
+        b1.record()
+        barrier()
+        bat_ms = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(bat_ms, op=dist.ReduceOp.MAX)
+        batched = {'points_per_launch': ev.batch_capacity(pts), 'points_per_flush': args.points, 'flushes': n_flush,
+                   'value': n_flush * args.points / (float(bat_ms[0]) * 1e-3), 'unit': 'evals/s',
+                   'loglike': bvals[-1],
+                   'mode': 'lanes of one ray march = (parameter point, realisation); one all-to-all and one '
+                           'chain of Gram phases per launch'}
+
     # ---- point-parallel mode (the reference's `_mpi_likelihood` decomposition): every rank
     # evaluates whole parameter points on its own, one small all-gather of the scalars per batch
     replicated = None
@@ -447,6 +470,7 @@ def main():
             'loglike': float(loglike),
             'exchange': {'mode': ev.exchange, 'note': ev.exchange_note},
             'pipelined': pipelined,
+            'batched': batched,
             'point_parallel': replicated,
         }
         if not args.no_cpu_baseline:

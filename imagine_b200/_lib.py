@@ -60,6 +60,8 @@ _SIGNATURES = {
     'imb_launch_count': (C.c_int64, []),
     'imb_field_eval': (C.c_int, [C.POINTER(Grid), C.POINTER(FieldDesc), C.c_int, _P, C.c_int, C.c_int,
                                  _P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
+    'imb_field_eval_lanes': (C.c_int, [C.POINTER(Grid), C.POINTER(FieldDesc), C.c_int, _P, C.c_int, C.c_int,
+                                       _P, C.c_int, C.c_int, C.c_int, _P]),
     'imb_field_rows': (C.c_int, [C.POINTER(FieldDesc), C.c_int, C.c_int, C.c_int]),
     'imb_test_simulate': (C.c_int, [C.POINTER(Grid), _P, C.c_int, C.c_int, _P, C.c_int, C.c_int,
                                     C.c_int, _P, C.c_int, C.c_double, _P, _P]),

@@ -33,6 +33,9 @@ struct FieldArgs {
   // order on the host (same IEEE additions the generic loop does), gauss = index of the Gaussian.
   int simple, has_const, gauss;
   double csum[3];
+  // interleaved output: lanes per group of the BUFFER (>= the RL of the thread mapping) and the first
+  // lane this call writes -- several parameter points share one wide buffer (imb_field_eval_lanes)
+  int out_rl, lane_off;
 };
 
 // the six normals of cell pair q of one realisation: v = [csum +] (z sigma + mu)
@@ -286,9 +289,10 @@ __global__ void __launch_bounds__(256) field_b_il_kernel(const __grid_constant__
     }
     const long long c0 = 2ll * q;
     const bool has2 = c0 + 1 < a.g.ncell;
-    double* o = out + ((long long)g * a.g.ncell + c0) * (3 * RL) + rl;
-    o[0] = v[0]; o[RL] = v[1]; o[2 * RL] = v[2];
-    if (has2) { o[3 * RL] = v[3]; o[4 * RL] = v[4]; o[5 * RL] = v[5]; }
+    const int orl = a.out_rl;                     // == RL unless the buffer is wider than this call's group
+    double* o = out + ((long long)g * a.g.ncell + c0) * (3 * orl) + a.lane_off + rl;
+    o[0] = v[0]; o[orl] = v[1]; o[2 * orl] = v[2];
+    if (has2) { o[3 * orl] = v[3]; o[4 * orl] = v[4]; o[5 * orl] = v[5]; }
   }
 }
 
@@ -545,10 +549,36 @@ int imb_field_rows(const imb_field_desc* fields, int nfields, int type, int n_re
   return rows;
 }
 
+static int field_eval_impl(const imb_grid* grid, const imb_field_desc* fields, int nfields,
+                           const uint64_t* seeds, int n_seed_rows, int n_real, double* out_B, int rows_B,
+                           int b_stride, int out_b_stride, int lane_offset, double* out_ne, int rows_ne,
+                           double* out_cre, int rows_cre, void* stream_);
+
 int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfields,
                    const uint64_t* seeds, int n_seed_rows, int n_real, double* out_B, int rows_B,
                    int b_stride, double* out_ne, int rows_ne, double* out_cre, int rows_cre,
                    void* stream_) {
+  return field_eval_impl(grid, fields, nfields, seeds, n_seed_rows, n_real, out_B, rows_B, b_stride, b_stride, 0,
+                         out_ne, rows_ne, out_cre, rows_cre, stream_);
+}
+
+int imb_field_eval_lanes(const imb_grid* grid, const imb_field_desc* fields, int nfields,
+                         const uint64_t* seeds, int n_seed_rows, int n_real, double* out_B, int b_stride,
+                         int out_b_stride, int lane_offset, void* stream_) {
+  if (!out_B || (b_stride != 24 && b_stride != 48 && b_stride != 96)) return IMB_EINVAL;
+  if ((out_b_stride != 48 && out_b_stride != 96) || out_b_stride < b_stride) return IMB_EINVAL;
+  const int rl = b_stride / 3, orl = out_b_stride / 3;
+  // ONE group of the thread mapping, landing inside one group of the buffer
+  if (n_real < 1 || n_real > rl || lane_offset < 0 || lane_offset % 8 != 0 || lane_offset + rl > orl)
+    return IMB_EINVAL;
+  return field_eval_impl(grid, fields, nfields, seeds, n_seed_rows, n_real, out_B, n_real, b_stride, out_b_stride,
+                         lane_offset, nullptr, 0, nullptr, 0, stream_);
+}
+
+static int field_eval_impl(const imb_grid* grid, const imb_field_desc* fields, int nfields,
+                           const uint64_t* seeds, int n_seed_rows, int n_real, double* out_B, int rows_B,
+                           int b_stride, int out_b_stride, int lane_offset, double* out_ne, int rows_ne,
+                           double* out_cre, int rows_cre, void* stream_) {
   IMB_TRY(check_init());
   IMB_TRY(upload_normal_tab());
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -606,6 +636,8 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
     }
     a.simple = a.has_const = a.gauss = 0;
     a.csum[0] = a.csum[1] = a.csum[2] = 0.0;
+    a.out_rl = out_b_stride / 3;
+    a.lane_off = lane_offset;
     if (type == 0) {
       int n_gauss = 0, n_const = 0;
       for (int f = 0; f < a.nfields; ++f) {

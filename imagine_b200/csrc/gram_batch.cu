@@ -21,7 +21,7 @@
 
 namespace imb {
 
-constexpr int KMAX = 16;           // observables per batch launch
+constexpr int KMAX = 32;           // keys per batch launch (observables x parameter points)
 // columns per Gram slice: fixed, so the summation order depends on m only (batching never changes a
 // key's value); 192 fills 148 SMs x 3 CTAs in 2.9 waves at C3 (5 keys x 256 slices), 256 left a third wave
 // that was 16 % full

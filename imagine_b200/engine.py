@@ -78,6 +78,16 @@ def field_rows(descs, n_real):
 
 
 FIELD_NAMES = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
+_FIELD_TYPE = {}
+
+
+def field_type(kind):
+    """0 magnetic field, 1 thermal electrons, 2 cosmic-ray electrons (what imb_field_rows says)."""
+    t = _FIELD_TYPE.get(kind)
+    if t is None:
+        rows = field_rows([(kind, [0.0], 0, 0)], 1)
+        t = _FIELD_TYPE[kind] = next(i for i in range(3) if rows[i] > 0)
+    return t
 
 
 INTERLEAVED_STRIDES = (24, 48, 96)
@@ -162,6 +172,25 @@ def field_eval(grid, descs, seeds, n_real=None, b_stride=4, out=None):
         C.byref(grid.c), arr, n, seeds.ctypes.data_as(C.c_void_p), int(seeds.shape[0]), n_real,
         L.ptr(B), rows[0], b_stride, L.ptr(ne), rows[1], L.ptr(cre), rows[2], L.stream_ptr()))
     return bufs
+
+
+def field_eval_lanes(grid, descs, seeds, n_real, b_stride, out_B, lane_offset):
+    """
+    imb_field_eval_lanes: the magnetic field of one parameter point into lanes [lane_offset, lane_offset +
+    b_stride / 3) of the wide interleaved buffer `out_B` [1, ncell, 3, RL_out] shared by several points.
+    """
+    L.init()
+    seeds = np.ascontiguousarray(np.atleast_2d(np.asarray(seeds, dtype=np.uint64)))
+    if seeds.shape[1] != n_real:
+        raise ValueError('need one seed per realisation (rows = seed lists)')
+    out_B = _f64(out_B, 'out_B')
+    if out_B.dim() != 4 or out_B.shape[0] != 1 or out_B.shape[1] != grid.ncell or out_B.shape[2] != 3:
+        raise ValueError('out_B must be [1, ncell, 3, RL]')
+    arr, n = L.make_field_descs(descs)
+    L.check(L.load().imb_field_eval_lanes(
+        C.byref(grid.c), arr, n, seeds.ctypes.data_as(C.c_void_p), int(seeds.shape[0]), int(n_real),
+        L.ptr(out_B), int(b_stride), 3 * int(out_B.shape[3]), int(lane_offset), L.stream_ptr()))
+    return out_B
 
 
 def test_simulate(grid, B, ne, n_real, points, b_axis=1, scale=1.0):
@@ -322,7 +351,7 @@ def _ptr_array(ts):
     return (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
 
 
-KMAX_BATCH = 16          # observables per batched launch (gram_batch.cu:KMAX)
+KMAX_BATCH = 32          # keys (observables x parameter points) per batched launch (gram_batch.cu:KMAX)
 
 
 def _check_key_views(tensors, name):

@@ -316,6 +316,112 @@ class EnsembleEvaluator:
             totals.append(t)
         return totals
 
+    # -- several parameter points per launch ----------------------------------------------------------
+    def batch_capacity(self, points=None):
+        """
+        How many parameter points one batched pass takes (0: batching does not apply).  The rays, cells
+        and trilinear weights of the march do not depend on the parameter point, so the lanes of a warp
+        can be (point, realisation) pairs: P points x n_local realisations fill the 32 lanes of the
+        fastest ray-march variant, where a sharded evaluation alone uses 8 or 16 of them in ray segments.
+        Needs the pixel-sharded exchange, at most 16 local realisations, a stochastic magnetic field and
+        -- because the march shares the (n_e, CRE) interpolants across its lanes -- identical
+        non-magnetic fields in every point of the batch (the usual GMF fit).
+        """
+        if self.exchange != 'alltoall' or self.n_local > 16:
+            return 0
+        lanes = 8 if self.n_local <= 8 else 16
+        cap = min(32 // lanes, engine.KMAX_BATCH // self.K)
+        if points is not None:
+            def scalar_part(descs):
+                return [(d[0], tuple(float(x) for x in d[1])) for d in descs if engine.field_type(d[0]) != 0]
+            first = scalar_part(points[0][0])
+            if any(scalar_part(d) != first for d, _ in points[1:]):
+                return 0
+            if any(engine.field_rows(d, 2)[0] != 2 for d, _ in points):
+                return 0                             # no stochastic magnetic field: nothing to interleave
+            if max(engine.field_rows(points[0][0], 2)[1:]) > 1:
+                return 0                             # per-realisation scalar grids
+        return cap if cap >= 2 else 0
+
+    def evaluate_batch(self, points, meas, var, estimator='oas'):
+        """
+        `evaluate_many` with up to `batch_capacity()` parameter points per LAUNCH: one field kernel per
+        point writes its lanes of a shared wide buffer (imb_field_eval_lanes), ONE ray march integrates all
+        points of the chunk, ONE all-to-all moves their maps and ONE chain of Gram phases (two all-reduces)
+        evaluates all points x observables keys.  Same realisations, same Philox keys as the one-point
+        path; the maps differ from it by rounding only (the one-point path splits a ray into segments per
+        warp at these shard sizes, this one does not).  Falls back to `evaluate_many` when batching does
+        not apply.  Returns one log-likelihood per point.
+        """
+        cap = self.batch_capacity(points)
+        if cap == 0 or len(points) < 2:
+            return self.evaluate_many(points, meas, var, estimator)
+        torch = self.torch
+        dev = self.dirs.device
+        f64 = torch.float64
+        lanes = 8 if self.n_local <= 8 else 16
+        qs = self.quantities
+        totals = []
+        pending = []
+        for c0 in range(0, len(points), cap):
+            chunk = points[c0:c0 + cap]
+            P = len(chunk)
+            rows = P * lanes                                  # rows of the shared ensemble (padded lanes incl.)
+            key = ('batch', rows)
+            bufs = self._field_bufs.get(key)
+            if bufs is None:
+                bufs = dict(B=torch.zeros((1, self.grid.ncell, 3, 32), dtype=f64, device=dev),
+                            send=torch.empty((self.world, self.K, rows, self.mp), dtype=f64, device=dev),
+                            G=torch.empty((P * self.K, self.n_real, self.n_real), dtype=f64, device=dev),
+                            P2=torch.empty((P * self.K, self.n_real * self.n_real + self.n_real + 4), dtype=f64,
+                                           device=dev))
+                bufs['recv'] = bufs['send'] if self.world == 1 else torch.empty_like(bufs['send'])
+                self._field_bufs[key] = bufs
+            # stage 1: the deterministic scalar grids once (shared by the chunk), B per point into its lanes
+            descs0, seeds0 = chunk[0]
+            scalar_descs = [d for d in descs0 if engine.field_type(d[0]) != 0]
+            shared = engine.field_eval(self.grid, scalar_descs, np.zeros((1, 1), dtype=np.uint64), n_real=1) \
+                if scalar_descs else {}
+            for p, (descs, seeds) in enumerate(chunk):
+                seeds = np.atleast_2d(np.asarray(seeds, dtype=np.uint64))
+                engine.field_eval_lanes(self.grid, [d for d in descs if engine.field_type(d[0]) == 0],
+                                        seeds[:, self.lo:self.hi], self.n_local, 3 * lanes, bufs['B'], p * lanes)
+            # stage 2: one march over (point, realisation) lanes, destination-major output
+            out = {LOS_OUTPUT[q]: bufs['send'][0, k] for k, q in enumerate(qs)}
+            engine.los_integrate(self.grid, self.settings, self.dirs, bufs['B'],
+                                 shared.get('thermal_electron_density'), shared.get('cosmic_ray_electron_density'),
+                                 n_real=rows, want=tuple(LOS_OUTPUT[q] for q in qs), out=out,
+                                 out_layout=(self.mp, self.K * rows * self.mp))
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_to_all_single(bufs['recv'], bufs['send'], group=self.group)
+            recv = bufs['recv']
+            # stage 3: P x K keys; key (p, k) = rows [p lanes, p lanes + n_local) of every source block
+            sims = [recv[0, k, p * lanes] for p in range(P) for k in range(self.K)]
+            layout = (self.n_local, self.K * rows * self.mp, self.mp)
+            meas_l = [meas[q][self.plo:self.phi] for q in qs] * P
+            var_l = [var[q][self.plo:self.phi] for q in qs] * P
+            vals = torch.empty((P * self.K,), dtype=f64, device=dev)
+            flags = torch.zeros((P * self.K,), dtype=torch.int32, device=dev)
+            engine.gram_phase1(sims, self.n_real, self.mp, layout, meas_l, bufs['G'])
+            self._allreduce(bufs['G'])
+            engine.gram_phase2(sims, self.n_real, self.mp, layout, meas_l, var_l, self.m, bufs['G'], bufs['P2'],
+                               estimator=estimator)
+            self._allreduce(bufs['P2'])
+            engine.gram_phase3_async(P * self.K, self.n_real, self.mp, bufs['G'], bufs['P2'], vals, flags)
+            pending.append((P, vals, flags))
+        for P, vals, flags in pending:                         # the host reads once per chunk, at the end
+            if bool(flags.cpu().any()):
+                raise np.linalg.LinAlgError('Gram route not applicable (non-positive shrunk diagonal); '
+                                            'evaluate these points with `evaluate`')
+            host = vals.cpu().reshape(P, self.K).tolist()
+            for row in host:
+                t = 0.0
+                for v in row:
+                    t += v
+                totals.append(t)
+        return totals
+
     def evaluate_points(self, points, meas, var, estimator='oas'):
         """
         Point-parallel evaluation: parameter point i is evaluated ENTIRELY on rank i % world (all N

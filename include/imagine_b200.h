@@ -145,6 +145,22 @@ int imb_field_eval(const imb_grid* grid, const imb_field_desc* fields, int nfiel
                    double* out_ne, int rows_ne,
                    double* out_cre, int rows_cre, void* stream);
 
+/*
+ * The magnetic field of ONE parameter point written into a slice of the lanes of a wider interleaved
+ * buffer, so that several parameter points share one buffer and ONE imb_los_integrate call marches
+ * them together (the rays, cells and trilinear weights do not depend on the parameter point; with n_local
+ * = 8 realisations per GPU and point, four points fill the 32 lanes of the fastest ray-march variant).
+ *   b_stride       24 | 48 | 96: lanes per group of THIS call (RL = b_stride / 3 >= n_real, one group)
+ *   out_b_stride   48 | 96 >= b_stride: the buffer is [1, ncell, 3, out_b_stride / 3]
+ *   lane_offset    first lane of this point (multiple of 8, lane_offset + RL <= out_b_stride / 3)
+ * Same arithmetic, same Philox keys as imb_field_eval: lane lane_offset + r holds realisation r bit for
+ * bit.  Only magnetic-type entries of `fields` are evaluated.  Asynchronous.
+ * (batched counterpart of Pipeline._core_likelihood over several cubes, pipelines/pipeline.py:976-979)
+ */
+int imb_field_eval_lanes(const imb_grid* grid, const imb_field_desc* fields, int nfields,
+                         const uint64_t* seeds, int n_seed_rows, int n_real,
+                         double* out_B, int b_stride, int out_b_stride, int lane_offset, void* stream);
+
 /* rows a field type needs: n_real if any stochastic field of `type` (0 B, 1 ne, 2 cre)
  * is in `fields`, 1 if only deterministic ones, 0 if none. HOST only, no CUDA work. */
 int imb_field_rows(const imb_field_desc* fields, int nfields, int type, int n_real);

@@ -97,6 +97,10 @@ def _worker(rank, world, port, queue):
         out['tiny_' + exchange] = ev.evaluate(DESCS, seeds, meas, var)
     ev, seeds, meas, var = _setup(rank, world, 'allgather')
     out['points'] = ev.evaluate_points(_points(seeds), meas, var)
+    # several points per launch on the sharded path: one march, one all-to-all, one chain of Gram phases
+    evb, seedsb, measb, varb = _setup(rank, world, 'alltoall')
+    out['batch_capacity'] = evb.batch_capacity(_points(seedsb))
+    out['batched'] = evb.evaluate_batch(_points(seedsb), measb, varb)
     # collectives behind the C ABI: the library's own NCCL communicator (the 128-byte id travels through
     # torch.distributed here; any host transport would do) runs the phased Gram route in ONE call
     from imagine_b200 import engine
@@ -155,6 +159,9 @@ def test_two_gpu_paths_match_single_gpu():
         assert out['peer'] == out['alltoall']                             # fused NVLink exchange: same data, same kernels
         assert out['plugin_sharded'] == 'ShardedDeviceObservable'
         assert out['points'] == want_points          # point-parallel mode: whole points per rank, bit-identical
+        assert out['batch_capacity'] == 4            # 8 local realisations: four points fill the 32 lanes
+        for a, b in zip(out['batched'], want_points):
+            assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (a, b)
         assert out['c_abi_collectives'] == out['alltoall']      # same phases, NCCL called by the library itself
         assert out['c_abi_allreduce'] == [3.0] * 5
         for mode in ('tiny_peer', 'tiny_allgather'):
@@ -166,3 +173,4 @@ def test_two_gpu_paths_match_single_gpu():
         assert np.allclose(out['plugin_full_Q'], q1, rtol=1e-9, atol=1e-12 * np.abs(q1).max())
     assert results[0][1]['alltoall'] == results[1][1]['alltoall']         # replicated scalar
     assert results[0][1]['plugin'] == results[1][1]['plugin']
+    assert results[0][1]['batched'] == results[1][1]['batched']
