@@ -268,7 +268,9 @@ __device__ __forceinline__ void generic_pair(const FieldArgs& a, unsigned int q,
 // of corners is one 128-bit load -- 4.95 vs 5.03 ms, twice the memory.)
 // SIMPLE: the list is constants + ONE Gaussian field (the usual case): its own instantiation, so that the
 // register budget of the hot kernel is not set by the analytic models of the generic path
-template <int RL, bool SIMPLE>
+// WIDE: the buffer's lane count and this call's first lane come from the arguments (imb_field_eval_lanes);
+// otherwise they are the compile-time RL and 0 (runtime strides cost the issue-bound kernel 4 %)
+template <int RL, bool SIMPLE, bool WIDE = false>
 __global__ void __launch_bounds__(256) field_b_il_kernel(const __grid_constant__ FieldArgs a,
                                                          double* __restrict__ out) {
   __shared__ double2 s_tab[kTabSize];
@@ -289,8 +291,8 @@ __global__ void __launch_bounds__(256) field_b_il_kernel(const __grid_constant__
     }
     const long long c0 = 2ll * q;
     const bool has2 = c0 + 1 < a.g.ncell;
-    const int orl = a.out_rl;                     // == RL unless the buffer is wider than this call's group
-    double* o = out + ((long long)g * a.g.ncell + c0) * (3 * orl) + a.lane_off + rl;
+    const int orl = WIDE ? a.out_rl : RL;
+    double* o = out + ((long long)g * a.g.ncell + c0) * (3 * orl) + (WIDE ? a.lane_off : 0) + rl;
     o[0] = v[0]; o[orl] = v[1]; o[2 * orl] = v[2];
     if (has2) { o[3 * orl] = v[3]; o[4 * orl] = v[4]; o[5 * orl] = v[5]; }
   }
@@ -665,7 +667,17 @@ static int field_eval_impl(const imb_grid* grid, const imb_field_desc* fields, i
         int bx = grid_blocks(((g.ncell + 1) / 2) * rl, 256, 8) / n_groups;
         if (bx < 1) bx = 1;
         const dim3 grid(bx, n_groups);
-        if (a.simple) {
+        const bool wide = out_b_stride != b_stride || lane_offset != 0;
+        if (wide) {
+          if (rl == 32) return IMB_EINVAL;
+          if (a.simple) {
+            if (rl == 16) field_b_il_kernel<16, true, true><<<grid, 256, 0, stream>>>(a, outs[type]);
+            else field_b_il_kernel<8, true, true><<<grid, 256, 0, stream>>>(a, outs[type]);
+          } else {
+            if (rl == 16) field_b_il_kernel<16, false, true><<<grid, 256, 0, stream>>>(a, outs[type]);
+            else field_b_il_kernel<8, false, true><<<grid, 256, 0, stream>>>(a, outs[type]);
+          }
+        } else if (a.simple) {
           if (rl == 32) field_b_il_kernel<32, true><<<grid, 256, 0, stream>>>(a, outs[type]);
           else if (rl == 16) field_b_il_kernel<16, true><<<grid, 256, 0, stream>>>(a, outs[type]);
           else field_b_il_kernel<8, true><<<grid, 256, 0, stream>>>(a, outs[type]);
