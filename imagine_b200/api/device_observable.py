@@ -12,6 +12,43 @@ import numpy as np
 from ._bases import Observable
 
 
+class _DeviceRows:
+    """
+    What `global_data` returns for a device-resident ensemble.  `Simulations.sub_sim` takes a row subset
+    with `self[k].global_data[indices, :]` and appends the result to a new `Simulations`
+    (observables/observable_dict.py:342-364; the likelihood convergence report, pipelines/pipeline.py:
+    1035-1124, does that for every ensemble size); `append` accepts an `Observable` as it is
+    (observable_dict.py:306-307), so indexing rows here returns a `DeviceObservable` of the subset and the
+    whole report stays on the device.  Every other use sees the host array.
+    """
+
+    def __init__(self, obs):
+        self._obs = obs
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple) and len(idx) == 2 and isinstance(idx[1], slice) and idx[1] == slice(None):
+            rows = np.arange(self._obs.shape[0])[idx[0]]
+            return self._obs.take_rows(np.atleast_1d(rows))
+        return self._obs.data[idx]
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self._obs.data, dtype=dtype)
+
+    def __len__(self):
+        return self._obs.shape[0]
+
+    @property
+    def shape(self):
+        return self._obs.shape
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float64)
+
+    def __getattr__(self, name):              # anything else NumPy-like: the host array
+        return getattr(self._obs.data, name)
+
+
 class DeviceObservable(Observable):
     def __init__(self, tensor, unit=None, coords=None, otype=None):
         assert tensor.dim() == 2, 'simulated observables are [ensemble, size]'
@@ -56,7 +93,7 @@ class DeviceObservable(Observable):
 
     @property
     def global_data(self):
-        return self.data
+        return _DeviceRows(self)
 
     @property
     def shape(self):

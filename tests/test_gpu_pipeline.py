@@ -150,3 +150,60 @@ def test_four_parameter_gmf_fit_through_the_reference_pipeline(env):
         chain = pipe(n_steps=25, step=0.1, seed=1, start=[0.8, 0.2, 0.7, 0.2], save_pipeline_state=False)
         assert chain[-1][1] > chain[0][1]                    # the walk climbs
         assert max(v for _, v in chain) <= at_truth + 50.0   # and nothing beats the truth by a wide margin
+
+
+def test_likelihood_convergence_report_stays_on_the_device(env):
+    """Pipeline.prepare_likelihood_convergence_report (pipelines/pipeline.py:1035-1124) with the drop-ins:
+    the reference's own loop -- simulate max_Nens * n_seeds realisations once, `Simulations.sub_sim` for
+    every ensemble size, likelihood + bootstrap dispersion for each -- where `sub_sim` hands out device
+    row subsets (no host copy of the maps is ever made).  Deterministic fields: identical to the
+    all-reference pipeline, NumPy draw for NumPy draw; Gaussian fields: a non-zero dispersion."""
+    api, img = env
+    u = api.units
+    import imagine.fields as RF
+    from imagine.simulators import TestSimulator
+    x = np.linspace(0.01, 2 * np.pi - 0.01, 10)
+    meas = _tabular_measurements(img, u, x, 3.0 * (1 + np.cos(x)), 0.1)
+    grid = img.fields.UniformGrid(box=[[0, 2 * np.pi] * u.kpc, [0, 0] * u.kpc, [0, 0] * u.kpc],
+                                  resolution=[100, 1, 1])
+    ne_params = {'n0': 1 * u.cm ** -3, 'a': 1 * u.rad / u.kpc, 'alpha': 0 * u.rad, 'b': 0 * u.rad / u.kpc,
+                 'beta': np.pi / 2 * u.rad, 'c': 0 * u.rad / u.kpc, 'gamma': np.pi / 2 * u.rad}
+
+    def build(ne_cls, b_cls, b_defaults, active, priors, sim_cls, lik_cls, rundir):
+        ne_f = img.fields.FieldFactory(field_class=ne_cls, grid=grid, default_parameters=ne_params)
+        b_f = img.fields.FieldFactory(field_class=b_cls, grid=grid, default_parameters=b_defaults,
+                                      active_parameters=active, priors=priors)
+        return _metropolis_pipeline(img)(simulator=sim_cls(meas), factory_list=[ne_f, b_f],
+                                        likelihood=lik_cls(meas), ensemble_size=4, run_directory=rundir,
+                                        show_summary_reports=False)
+
+    const = dict(b_defaults={'Bx': 0 * u.microgauss, 'By': 3 * u.microgauss, 'Bz': 0 * u.microgauss},
+                 active=('By',), priors={'By': img.priors.FlatPrior(xmin=0 * u.microgauss, xmax=6 * u.microgauss)})
+    kw = dict(min_Nens=3, max_Nens=5, n_seeds=2, n_points=2)
+    with tempfile.TemporaryDirectory() as d1, tempfile.TemporaryDirectory() as d2, tempfile.TemporaryDirectory() as d3:
+        ref = build(RF.CosThermalElectronDensity, RF.ConstantMagneticField, sim_cls=TestSimulator,
+                    lik_cls=img.likelihoods.EnsembleLikelihood, rundir=d1, **const)
+        gpu = build(api.CosThermalElectronDensity, api.ConstantMagneticField, sim_cls=api.B200TestSimulator,
+                    lik_cls=api.B200EnsembleLikelihood, rundir=d2, **const)
+        np.random.seed(11)
+        want = ref.prepare_likelihood_convergence_report(**kw)
+        np.random.seed(11)
+        got = gpu.prepare_likelihood_convergence_report(**kw)
+        assert list(got['ensemble_size']) == list(want['ensemble_size']) and len(got) == 2 * 2 * 3
+        assert np.allclose(got['likelihood'], want['likelihood'], rtol=0, atol=1e-8)
+        assert np.allclose(got['likelihood_std'], want['likelihood_std'], rtol=0, atol=1e-8)
+        assert gpu.ensemble_size == 4 and gpu.likelihood.compute_dispersion is False      # settings restored
+
+        gauss = dict(b_defaults={'a0': 3 * u.microgauss, 'b0': 0.5 * u.microgauss}, active=('a0',),
+                     priors={'a0': img.priors.FlatPrior(xmin=0 * u.microgauss, xmax=6 * u.microgauss)})
+        rnd = build(api.CosThermalElectronDensity, api.NaiveGaussianMagneticField, sim_cls=api.B200TestSimulator,
+                    lik_cls=api.B200EnsembleLikelihood, rundir=d3, **gauss)
+        seen = []
+        inner = rnd._get_observables
+        rnd._get_observables = lambda values: seen.append(inner(values)) or seen[-1]
+        report = rnd.prepare_likelihood_convergence_report(min_Nens=4, max_Nens=8, n_seeds=1, n_points=1)
+        assert np.all(np.isfinite(report['likelihood'])) and np.all(report['likelihood_std'] > 0)
+        key = next(iter(seen[0].keys()))
+        sub = seen[0].sub_sim(slice(0, 3))[key]
+        assert type(sub).__name__ == 'DeviceObservable' and sub.shape[0] == 3
+        assert seen[0][key]._host is None               # the maps never left the device during the report
