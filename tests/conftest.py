@@ -9,6 +9,7 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    config.addinivalue_line('markers', 'quick: marker used by the reference test files that tests/test_gpu_reference_suite.py loads')
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
