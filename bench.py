@@ -473,7 +473,7 @@ def main():
             'batched': batched,
             'point_parallel': replicated,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # the CPU leg is timed at N = 1 only
             try:
                 line['cpu_baseline'] = cpu_baseline_object(cpu_reference(args.workload))
             except Exception as exc:                                      # never lose the GPU line
