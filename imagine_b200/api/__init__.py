@@ -17,5 +17,6 @@ from .fields import (CosmicRayElectronDensityField, ConstantMagneticField, Naive
                      RandomThermalElectrons, CosThermalElectronDensity,
                      AnalyticCosmicRayElectrons, ConstantCosmicRayElectrons)
 from .simulators import B200Simulator, B200TestSimulator                               # noqa: F401
+from .vectorized import VectorizedLikelihood                                           # noqa: F401
 from .likelihoods import (B200EnsembleLikelihood, B200EnsembleLikelihoodDiagonal,      # noqa: F401
                           B200SimpleLikelihood)

@@ -317,6 +317,20 @@ def test_phased_route_refuses_a_workspace_somebody_else_used(eng):
     assert eng.gram_phase3(K, N, m, G, P2) == want
 
 
+def test_unit_scaling_law(eng):
+    """Expressing maps, measurements and variances in a unit s times smaller shifts the log-likelihood by
+    -m log s (the determinant term): what api.VectorizedLikelihood uses to work in the kernels' units."""
+    rng = np.random.default_rng(21)
+    N, m, s = 12, 300, 1e3
+    sims = rng.normal(size=(N, m)) + 2.0
+    meas = rng.normal(size=m) + 2.0
+    var = rng.uniform(0.5, 1.5, size=m)
+    for est in ('oas', 'empirical'):
+        base = eng.loglike_ensemble(_dev(sims), _dev(meas), _dev(var), estimator=est)
+        scaled = eng.loglike_ensemble(_dev(sims * s), _dev(meas * s), _dev(var * s * s), estimator=est)
+        assert abs(scaled - (base - m * np.log(s))) <= 1e-8 * max(1.0, abs(base))
+
+
 def test_edge_shapes(eng):
     """Smallest / ragged inputs: one pixel, one realisation, empty masks, N >> m."""
     import torch

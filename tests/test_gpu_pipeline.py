@@ -147,6 +147,16 @@ def test_four_parameter_gmf_fit_through_the_reference_pipeline(env):
         at_truth = ll([0.5, 0.5, 0.4833333333333333, 0.5])
         far = ll([0.95, 0.05, 0.9, 0.05])
         assert np.isfinite(at_truth) and at_truth > far
+        # several cubes per call (what a vectorised sampler hands over): fields, priors, seeds and rescaler
+        # are the pipeline's own, the points share one ray march over (point, realisation) lanes
+        vec = api.VectorizedLikelihood(pipe)
+        cubes = np.array([pipe.prior_transform(np.array(c)) for c in
+                          ([0.5, 0.5, 0.48, 0.5], [0.95, 0.05, 0.9, 0.05], [0.3, 0.6, 0.2, 0.7],
+                           [0.6, 0.4, 0.5, 0.5], [0.1, 0.9, 0.4, 0.2])])
+        one_by_one = np.array([pipe._likelihood_function(c) for c in cubes])
+        together = vec(cubes)
+        assert vec._ev.batch_capacity() == 4 and together.shape == (5,)
+        assert np.allclose(together, one_by_one, rtol=1e-9, atol=1e-8), (together, one_by_one)
         chain = pipe(n_steps=25, step=0.1, seed=1, start=[0.8, 0.2, 0.7, 0.2], save_pipeline_state=False)
         assert chain[-1][1] > chain[0][1]                    # the walk climbs
         assert max(v for _, v in chain) <= at_truth + 50.0   # and nothing beats the truth by a wide margin
