@@ -28,6 +28,10 @@ Two exchange modes between the simulation and the likelihood:
 
 Either way every rank returns the identical scalar ("copied to all nodes",
 likelihoods/ensemble_likelihood.py:79-80).
+
+Several parameter points at once: `evaluate_many` (asynchronous pipelining), `evaluate_batch` (up to four
+points per LAUNCH: the lanes of the ray march are (point, realisation) pairs, one exchange and one chain of
+Gram phases for points x observables keys), `evaluate_points` (one point per GPU).
 """
 import logging
 
@@ -175,6 +179,7 @@ class EnsembleEvaluator:
                                   for q in self.quantities}
             else:
                 self.full_maps = self.local_maps
+                self.mp, self.plo, self.phi = self.m, 0, self.m      # evaluate_batch: one "shard" = everything
 
     def _init_peer_buffers(self, dev):
         """Receive buffer [P(source), K, n_local, m/P] in NVLink symmetric memory + peer offsets."""
@@ -323,11 +328,11 @@ class EnsembleEvaluator:
         and trilinear weights of the march do not depend on the parameter point, so the lanes of a warp
         can be (point, realisation) pairs: P points x n_local realisations fill the 32 lanes of the
         fastest ray-march variant, where a sharded evaluation alone uses 8 or 16 of them in ray segments.
-        Needs the pixel-sharded exchange, at most 16 local realisations, a stochastic magnetic field and
+        Needs the pixel-sharded exchange (or a single GPU), at most 16 local realisations, a stochastic magnetic field and
         -- because the march shares the (n_e, CRE) interpolants across its lanes -- identical
         non-magnetic fields in every point of the batch (the usual GMF fit).
         """
-        if self.exchange != 'alltoall' or self.n_local > 16:
+        if not (self.exchange == 'alltoall' or self.world == 1) or self.n_local > 16:
             return 0
         lanes = 8 if self.n_local <= 8 else 16
         cap = min(32 // lanes, engine.KMAX_BATCH // self.K)

@@ -75,3 +75,13 @@ def test_batching_steps_aside_when_it_does_not_apply(lib):
     assert np.allclose(ev.evaluate_batch(mixed, meas, var), want, rtol=1e-12)
     ev32, seeds32, meas32, var32 = _setup(0, 1, 'alltoall', N=32)
     assert ev32.batch_capacity() == 0                            # 32 local realisations already fill the warp
+
+
+def test_single_gpu_evaluator_batches_whatever_its_exchange_mode(lib):
+    ev, seeds, meas, var = _setup(0, 1, 'auto', N=16)            # world = 1: 'auto' is the all-gather layout
+    assert ev.exchange == 'allgather' and ev.batch_capacity() == 2
+    pts = _points(seeds, (0.5, 1.0, 2.0))
+    one = [ev.evaluate(d, s, meas, var) for d, s in pts]
+    got = ev.evaluate_batch(pts, meas, var)
+    for a, b in zip(got, one):
+        assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (a, b)
