@@ -74,9 +74,12 @@ class _DeviceFieldMixin:
 
     def _canonical_parameters(self):
         vals = []
+        params = self.parameters             # the reference's getter validates on every access: once
         for name, unit in zip(self.PARAMETER_NAMES, self.PARAM_UNITS):
-            p = self.parameters[name]
-            if isinstance(p, u.Quantity):
+            p = params[name]
+            if isinstance(p, u.Quantity) and p.unit is unit:
+                p = p.value                  # already canonical (the usual case): no conversion
+            elif isinstance(p, u.Quantity):
                 try:
                     p = p.to_value(unit)
                 except Exception:            # e.g. 1/kpc given where rad/kpc is expected

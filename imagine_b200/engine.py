@@ -71,10 +71,19 @@ class LosSettings:
 
 
 # --------------------------------------------------------------------------------- stage 1
+_FIELD_ROWS = {}
+
+
 def field_rows(descs, n_real):
-    arr, n = L.make_field_descs(descs)
-    lib = L.load()
-    return tuple(lib.imb_field_rows(arr, n, t, n_real) for t in range(3))
+    """Rows per field type (imb_field_rows): a function of the kinds and n_real only -- memoised, a sampler
+    asks the same question ten thousand times."""
+    key = (tuple(int(d[0]) for d in descs), int(n_real))
+    rows = _FIELD_ROWS.get(key)
+    if rows is None:
+        arr, n = L.make_field_descs(descs)
+        lib = L.load()
+        rows = _FIELD_ROWS[key] = tuple(lib.imb_field_rows(arr, n, t, n_real) for t in range(3))
+    return rows
 
 
 FIELD_NAMES = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
