@@ -400,6 +400,7 @@ def main():
         import pstats
         prof.disable()
         pstats.Stats(prof, stream=sys.stderr).sort_stats('cumulative').print_stats(45)
+        pstats.Stats(prof, stream=sys.stderr).sort_stats('tottime').print_stats(25)
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 0.0)
