@@ -96,6 +96,7 @@ _SIGNATURES = {
     'imb_comm_size': (C.c_int, []),
     'imb_comm_rank': (C.c_int, []),
     'imb_allreduce_sum': (C.c_int, [_P, C.c_int64, _P]),
+    'imb_alltoall': (C.c_int, [_P, _P, C.c_int64, _P]),
     'imb_loglike_ensemble_sharded': (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                                _P, _P, C.c_int64, C.c_int, _P, _P, C.POINTER(C.c_double),
                                                C.POINTER(C.c_int32), _P]),

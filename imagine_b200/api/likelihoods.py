@@ -250,11 +250,17 @@ class B200EnsembleLikelihood(_DeviceLikelihoodMixin, Likelihood):
                                 'G': torch.empty((K, N, N), dtype=torch.float64, device='cuda'),
                                 'P2': torch.empty((K, N * N + N + 4), dtype=torch.float64, device='cuda')}
         G, P2 = self._shard_bufs['G'], self._shard_bufs['P2']
-        engine.gram_phase1(sims, N, mp, o0.row_layout, meas, G)
-        dist.all_reduce(G, op=dist.ReduceOp.SUM, group=o0.group)
-        engine.gram_phase2(sims, N, mp, o0.row_layout, meas, var, o0.m, G, P2, estimator=self.estimator)
-        dist.all_reduce(P2, op=dist.ReduceOp.SUM, group=o0.group)
-        vals = engine.gram_phase3(K, N, mp, G, P2)
+        from ..hotpath import ensure_library_comm
+        if ensure_library_comm(o0.rank, o0.world, o0.group):
+            # phases and both all-reduces in ONE library call on the kernels' stream (csrc/comm.cu)
+            vals = engine.loglike_ensemble_sharded(sims, N, mp, o0.row_layout, meas, var, o0.m, G, P2,
+                                                   estimator=self.estimator)
+        else:
+            engine.gram_phase1(sims, N, mp, o0.row_layout, meas, G)
+            dist.all_reduce(G, op=dist.ReduceOp.SUM, group=o0.group)
+            engine.gram_phase2(sims, N, mp, o0.row_layout, meas, var, o0.m, G, P2, estimator=self.estimator)
+            dist.all_reduce(P2, op=dist.ReduceOp.SUM, group=o0.group)
+            vals = engine.gram_phase3(K, N, mp, G, P2)
         total = 0.
         for v in vals:
             total += v

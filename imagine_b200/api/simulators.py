@@ -28,7 +28,7 @@ from ._bases import Simulator, Simulations, Masks
 from .device_observable import DeviceObservable, ShardedDeviceObservable
 from .fields import descriptor_of, device_grid
 from .. import engine
-from ..hotpath import PeerExchange, exchange_pixel_shards, gather_rows, shard_bounds
+from ..hotpath import PeerExchange, exchange_pixel_shards, ensure_library_comm, gather_rows, shard_bounds
 
 FIELD_UNITS = {'magnetic_field': u.microgauss, 'thermal_electron_density': u.cm ** -3}
 _NAMES = ('magnetic_field', 'thermal_electron_density', 'cosmic_ray_electron_density')
@@ -402,6 +402,7 @@ class B200Simulator(Simulator):
             send = self._send
             views = {key: send[0, k] for k, key in enumerate(self.observables)}
             self._integrate(dg, dev_fields, n_local, sharded=(views, (mp, K * n_local * mp)))
+            ensure_library_comm(self.rank, self.world, self.group)     # once; then the library's all-to-all
             recv = exchange_pixel_shards(send, self.group)
         sims = Simulations()
         for k, key in enumerate(self.observables):

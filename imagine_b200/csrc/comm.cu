@@ -7,6 +7,9 @@
 //   imb_comm_init        every rank joins; one communicator per process (= per GPU)
 //   imb_allreduce_sum    SUM all-reduce of doubles in place -- the reference's `mpi_mean` /
 //                        `Allreduce` building block (tools/mpi_helper.py:132)
+//   imb_alltoall         block r of `send` goes to rank r, block q of `recv` comes from rank q (grouped
+//                        ncclSend / ncclRecv on the caller's stream): the exchange of the simulated maps
+//                        [P(dest), K, n_local, m/P] -> [P(source), K, n_local, m/P]
 //   imb_loglike_ensemble_sharded
 //                        EnsembleLikelihood.call (likelihoods/ensemble_likelihood.py:68-107) for K keys
 //                        whose PIXELS are sharded over the ranks: phase 1 -> all-reduce G -> phase 2 ->
@@ -26,6 +29,8 @@ typedef int (*fn_init_rank)(ncclComm_t*, int, NcclId, int);
 typedef int (*fn_destroy)(ncclComm_t);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
 typedef const char* (*fn_errstr)(int);
+typedef int (*fn_sendrecv)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);   // ncclSend (ncclRecv: void*)
+typedef int (*fn_group)(void);
 
 struct Nccl {
   void* handle = nullptr;
@@ -34,6 +39,8 @@ struct Nccl {
   fn_destroy destroy = nullptr;
   fn_allreduce allreduce = nullptr;
   fn_errstr errstr = nullptr;
+  fn_sendrecv send = nullptr, recv = nullptr;
+  fn_group group_start = nullptr, group_end = nullptr;
   ncclComm_t comm = nullptr;
   int nranks = 0, rank = -1;
 };
@@ -67,7 +74,12 @@ static int load_nccl() {
   n.destroy = (fn_destroy)dlsym(n.handle, "ncclCommDestroy");
   n.allreduce = (fn_allreduce)dlsym(n.handle, "ncclAllReduce");
   n.errstr = (fn_errstr)dlsym(n.handle, "ncclGetErrorString");
-  if (!n.get_id || !n.init_rank || !n.destroy || !n.allreduce) {
+  n.send = (fn_sendrecv)dlsym(n.handle, "ncclSend");
+  n.recv = (fn_sendrecv)dlsym(n.handle, "ncclRecv");
+  n.group_start = (fn_group)dlsym(n.handle, "ncclGroupStart");
+  n.group_end = (fn_group)dlsym(n.handle, "ncclGroupEnd");
+  if (!n.get_id || !n.init_rank || !n.destroy || !n.allreduce || !n.send || !n.recv || !n.group_start ||
+      !n.group_end) {
     snprintf(state().cuda_err, sizeof(state().cuda_err), "libnccl lacks a required symbol");
     return IMB_EUNSUPPORTED;
   }
@@ -135,6 +147,24 @@ int imb_allreduce_sum(double* device_buf, int64_t count, void* stream) {
   if (!device_buf || count < 0) return IMB_EINVAL;
   if (count == 0) return IMB_OK;
   return allreduce_sum(device_buf, (size_t)count, (cudaStream_t)stream);
+}
+
+int imb_alltoall(const double* send, double* recv, int64_t count_per_rank, void* stream) {
+  IMB_TRY(check_init());
+  Nccl& n = nccl();
+  if (!n.comm) return IMB_ENOTINIT;
+  if (!send || !recv || count_per_rank < 0) return IMB_EINVAL;
+  if (count_per_rank == 0) return IMB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = n.group_start();
+  if (rc != 0) return nccl_error(rc, "ncclGroupStart");
+  for (int r = 0; r < n.nranks && rc == 0; ++r) {
+    rc = n.send(send + (size_t)r * count_per_rank, (size_t)count_per_rank, 8, r, n.comm, s);
+    if (rc == 0) rc = n.recv(recv + (size_t)r * count_per_rank, (size_t)count_per_rank, 8, r, n.comm, s);
+  }
+  const int rc_end = n.group_end();
+  if (rc != 0) return nccl_error(rc, "ncclSend/ncclRecv");
+  return rc_end == 0 ? IMB_OK : nccl_error(rc_end, "ncclGroupEnd");
 }
 
 int imb_loglike_ensemble_sharded(int K, const double* const* sims, int N, int m_local,

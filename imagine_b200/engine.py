@@ -441,6 +441,21 @@ def comm_finalize():
     L.check(L.load().imb_comm_finalize())
 
 
+def comm_size():
+    """Ranks of the library's own communicator (0: not initialised)."""
+    return int(L.load().imb_comm_size())
+
+
+def alltoall(send, recv):
+    """imb_alltoall: block r of `send` [P, ...] to rank r, block q of `recv` from rank q (same stream)."""
+    _check_key_views([send, recv], 'send / recv')
+    P = send.shape[0]
+    if send.shape != recv.shape or send.data_ptr() == recv.data_ptr() or send.numel() % P:
+        raise ValueError('send and recv must be distinct [P, ...] tensors of one shape')
+    L.check(L.load().imb_alltoall(L.ptr(send), L.ptr(recv), send.numel() // P, L.stream_ptr()))
+    return recv
+
+
 def allreduce_sum(t):
     """In-place SUM all-reduce of a CUDA float64 tensor over the library's own communicator."""
     _check_key_views([t], 'tensor')

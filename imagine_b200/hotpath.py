@@ -75,6 +75,49 @@ def gather_rows(local, n_real, group=None):
     return full
 
 
+_LIBRARY_COMM = {'tried': False, 'ok': False}
+
+
+def ensure_library_comm(rank, world, group=None):
+    """
+    Initialise the library's OWN NCCL communicator (csrc/comm.cu) next to torch.distributed's, once per
+    process: the all-to-all and the two all-reduces of a sharded evaluation then run as plain library calls
+    on the kernels' stream -- no cross-stream events, a fraction of torch.distributed's host cost per
+    collective (at 8 GPUs one evaluation is 1.1 ms, the host side of the plugin path about as much).
+    The 128-byte id travels through a torch.distributed broadcast.  Every rank first reports whether it
+    can load NCCL at all, so a rank that cannot never leaves the others waiting in the init.  Returns
+    True when the library communicator spans exactly the default group's ranks; IMB_LIBRARY_COLLECTIVES=0
+    switches it off.
+    """
+    import os
+    import torch
+    import torch.distributed as dist
+    if world <= 1 or group is not None or os.environ.get('IMB_LIBRARY_COLLECTIVES', '1') == '0':
+        return False
+    if _LIBRARY_COMM['tried']:
+        return _LIBRARY_COMM['ok'] and engine.comm_size() == world
+    _LIBRARY_COMM['tried'] = True
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() != world:
+        return False
+    dev = torch.device('cuda', torch.cuda.current_device())
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    can = torch.ones(1, dtype=torch.int32, device=dev)
+    try:
+        uid = engine.comm_unique_id()                    # loads NCCL; only rank 0's id is used
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(uid), dtype=torch.uint8).to(dev)
+    except Exception as exc:
+        can.zero_()
+        log.warning('library collectives unavailable on rank %d: %s', rank, exc)
+    dist.all_reduce(can, op=dist.ReduceOp.MIN)
+    if int(can.item()) == 0:
+        return False
+    dist.broadcast(idt, 0)
+    engine.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
+    _LIBRARY_COMM['ok'] = True
+    return True
+
+
 def exchange_pixel_shards(send, group=None):
     """
     All-to-all of a destination-major buffer [P, K, n_local, m/P]: block p goes to rank p; the
@@ -86,6 +129,8 @@ def exchange_pixel_shards(send, group=None):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return send
     recv = torch.empty_like(send)
+    if send.is_cuda and group is None and _LIBRARY_COMM['ok'] and engine.comm_size() == send.shape[0]:
+        return engine.alltoall(send, recv)
     dist.all_to_all_single(recv, send, group=group)
     return recv
 
@@ -133,7 +178,8 @@ class EnsembleEvaluator:
         self.dirs = engine.healpix_ring_dirs(self.nside)
         self._field_bufs = {}
         self._local = None                          # world = 1 evaluator of evaluate_points
-        self.library_collectives = False            # True: all-reduces through imb_comm_* instead of torch
+        # collectives through the library's own communicator (imb_comm_*) instead of torch.distributed
+        self.library_collectives = ensure_library_comm(self.rank, self.world, group)
         dev = self.dirs.device
         shardable = self.world > 1 and self.m % self.world == 0 and self.world <= 16
         if exchange == 'auto':
@@ -235,8 +281,7 @@ class EnsembleEvaluator:
             return self.recv
         if self.exchange == 'alltoall':
             if self.world > 1:
-                import torch.distributed as dist
-                dist.all_to_all_single(self.recv, self.send, group=self.group)
+                self._alltoall(self.send, self.recv)
             return self.recv
         if self.world == 1:
             return self.local_maps
@@ -259,7 +304,7 @@ class EnsembleEvaluator:
             layout = (self.n_local, self.K * self.n_local * self.mp, self.mp)
             meas_l = [meas[q][self.plo:self.phi] for q in qs]
             var_l = [var[q][self.plo:self.phi] for q in qs]
-            if self.library_collectives:           # phases + all-reduces inside the library (csrc/comm.cu)
+            if self.library_collectives and engine.comm_size() == self.world:   # phases + all-reduces inside the library (csrc/comm.cu)
                 vals = engine.loglike_ensemble_sharded(sims, self.n_real, self.mp, layout, meas_l, var_l, self.m,
                                                        self.G, self.P2, estimator=estimator)
             else:
@@ -398,8 +443,7 @@ class EnsembleEvaluator:
                                  n_real=rows, want=tuple(LOS_OUTPUT[q] for q in qs), out=out,
                                  out_layout=(self.mp, self.K * rows * self.mp))
             if self.world > 1:
-                import torch.distributed as dist
-                dist.all_to_all_single(bufs['recv'], bufs['send'], group=self.group)
+                self._alltoall(bufs['send'], bufs['recv'])
             recv = bufs['recv']
             # stage 3: P x K keys; key (p, k) = rows [p lanes, p lanes + n_local) of every source block
             sims = [recv[0, k, p * lanes] for p in range(P) for k in range(self.K)]
@@ -459,8 +503,18 @@ class EnsembleEvaluator:
 
     def _allreduce(self, t):
         if self.world > 1:
+            if self.library_collectives and engine.comm_size() == self.world:
+                engine.allreduce_sum(t)
+                return
             import torch.distributed as dist
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _alltoall(self, send, recv):
+        if self.library_collectives and engine.comm_size() == self.world:
+            engine.alltoall(send, recv)
+            return
+        import torch.distributed as dist
+        dist.all_to_all_single(recv, send, group=self.group)
 
     def evaluate(self, descs, seeds, meas, var, estimator='oas'):
         self.simulate(descs, seeds)

@@ -289,6 +289,13 @@ int imb_comm_finalize(void);
 int imb_comm_size(void);
 int imb_comm_rank(void);
 int imb_allreduce_sum(double* device_buf, int64_t count, void* stream);
+/* All-to-all of doubles on the library's communicator: block r (count_per_rank doubles) of `send` goes to
+ * rank r, block q of `recv` arrives from rank q; `recv` must not alias `send`.  The exchange of the
+ * destination-major map buffer the ray march writes (imb_los_cfg.out_cols_per_dest): afterwards every rank
+ * holds all realisations of its pixels (mpi_helper.py's distributed arrays, tools/mpi_helper.py:25-90).
+ * Asynchronous on `stream`. */
+int imb_alltoall(const double* send, double* recv, int64_t count_per_rank, void* stream);
+
 int imb_loglike_ensemble_sharded(int K, const double* const* sims, int N, int m_local,
                                  int rows_per_block, int64_t block_stride, int64_t row_stride,
                                  const double* const* meas, const double* const* var, int64_t m_total,
