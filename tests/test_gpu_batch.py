@@ -6,7 +6,7 @@ the parameter point (batched counterpart of the loop over cubes in pipelines/pip
 import numpy as np
 import pytest
 
-from tests.test_gpu_multirank import BOX, DESCS, NSIDE, QUANT, RES, _setup
+from tests.test_gpu_multirank import BOX, DESCS, RES, _setup
 
 pytestmark = pytest.mark.gpu
 
