@@ -28,3 +28,20 @@ def sync_coefficient(p, nu_ghz, e0_gev):
     c_gamma = ((4.0 * math.pi / C_LIGHT) * (e0_gev * GEV_ERG) ** p
                * MEC2_ERG ** (1.0 - p) / (GEV_ERG * 1.0e4))
     return t_conv * 0.5 * ptot * c_gamma * (1.0e-6) ** ((p + 1.0) / 2.0)
+
+
+H_PLANCK = 6.62607015e-27      # erg s
+T_CMB = 2.725                  # K
+
+
+def rj_to_cmb(nu_ghz, t_cmb=T_CMB):
+    """
+    Factor from Rayleigh-Jeans brightness temperature (what the kernels integrate) to thermodynamic CMB
+    temperature: dT_CMB = dT_RJ (e^x - 1)^2 / (x^2 e^x), x = h nu / (k T_cmb).  The reference's key
+    convention is K-cmb (observables/observable_dict.py:15-19) and the hammurabiX output recorded in
+    tutorials/tutorial_hammurabi.ipynb is reproduced to 3e-5 with this factor (1.01375 at 23 GHz) --
+    tools/hammurabi_tutorial_pin.py.
+    """
+    x = H_PLANCK * nu_ghz * 1.0e9 / (K_B * t_cmb)
+    ex = math.exp(x)
+    return (ex - 1.0) ** 2 / (x * x * ex)

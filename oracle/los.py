@@ -1,11 +1,15 @@
 """
 CPU oracle, stage 2: line-of-sight integration of gridded fields to sky maps.
 
-PARITY UNPINNED BY THE REFERENCE.  IMAGINE delegates this arithmetic to the external
-C++ program hammurabiX v2.4.2 (docker/Dockerfile:42, requirements.txt:9 `hampyx>=2.4.0`;
+PARITY: STOKES I PINNED, THE REST UNPINNED BY THE REFERENCE.  IMAGINE delegates this arithmetic to the
+external C++ program hammurabiX v2.4.2 (docker/Dockerfile:42, requirements.txt:9 `hampyx>=2.4.0`;
 call sites simulators/hammurabi.py:83,207,212).  Its source is not under /root/reference
-and no reference test exercises it, so this file *defines* the result and
-is pinned only by analytic closed forms (tests/test_oracle_los.py).  What the reference
+and no reference test exercises it, so this file *defines* the result.  It is pinned by
+analytic closed forms (tests/test_oracle_los.py) and -- total intensity only -- by the one hammurabiX
+output the reference records (tutorials/tutorial_hammurabi.ipynb cell 14: Stokes I of the built-in LSA +
+analytic CRE models, reproduced to 3e-5 after the K_RJ -> K_CMB conversion `rj_to_cmb`;
+tools/hammurabi_tutorial_pin.py, test_tutorial_hammurabi_pin).  Faraday depth sign and the Q/U convention
+have no recorded output to compare with (docs/los_conventions.md).  What the reference
 does fix, and this file follows:
   * observable keys / units: fd [rad m^-2], dm [pc cm^-3], sync I/Q/U/PI [K], PA [rad]
     (simulators/hammurabi.py:56, 214-227; observables/observable_dict.py:11-25, IAU Q/U)
@@ -58,6 +62,17 @@ def sync_coefficient(p, nu_ghz, e0_gev):
 
 def pol_fraction(p):
     return (p + 1.0) / (p + 7.0 / 3.0)
+
+
+H_PLANCK = 6.62607015e-27      # erg s
+T_CMB = 2.725                  # K
+
+
+def rj_to_cmb(nu_ghz, t_cmb=T_CMB):
+    """dT_CMB / dT_RJ = (e^x - 1)^2 / (x^2 e^x), x = h nu / (k T_cmb): hammurabiX reports K-cmb
+    (observables/observable_dict.py:15-19; pinned by tools/hammurabi_tutorial_pin.py)."""
+    x = H_PLANCK * nu_ghz * 1.0e9 / (K_B * t_cmb)
+    return (np.exp(x) - 1.0) ** 2 / (x * x * np.exp(x))
 
 
 def lambda_sq_m2(nu_ghz):

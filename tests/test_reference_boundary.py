@@ -105,3 +105,23 @@ def test_reference_fields_reproduce_the_tutorial_goldens_with_the_units_stand_in
     got = np.asarray(ne.get_data()[3:5, 3:5, 3:5].to_value(u.cm ** -3)).ravel()
     want = [0.00189093, 0.00361981, 0.00289678, 0.0055453, 0.00289678, 0.0055453, 0.00473694, 0.00906791]
     assert np.allclose(got, want, rtol=0, atol=5e-9)
+
+
+def test_simulator_can_report_thermodynamic_temperature():
+    """hammurabiX (and the reference's key convention, observable_dict.py:15-19) reports K-cmb; the kernels
+    integrate Rayleigh-Jeans brightness temperature.  `temperature='cmb'` applies the conversion to the
+    synchrotron maps through the same per-key scale as unit conversions."""
+    import imagine_b200.api as api
+    from imagine_b200.constants import rj_to_cmb
+    u = api.units
+    M = api.Measurements()
+    keys = [('fd', None, 2, None), ('sync', 23.0, 2, 'I'), ('sync', 23.0, 2, 'Q'), ('sync', 1.4, 2, 'PA')]
+    units = [u.rad / u.m ** 2, u.K, u.K, u.rad]
+    for k, un in zip(keys, units):
+        M.append(name=k, data=np.zeros((1, 48)) * un, otype='HEALPix')
+    rj, cmb = api.B200Simulator(M), api.B200Simulator(M, temperature='cmb')
+    assert [rj._scale(k) for k in keys] == [1.0, 1.0, 1.0, 1.0]
+    assert [cmb._scale(k) for k in keys] == [1.0, rj_to_cmb(23.0), rj_to_cmb(23.0), 1.0]
+    assert abs(rj_to_cmb(23.0) - 1.01375) < 1e-5 and abs(rj_to_cmb(1.4) - 1.00005) < 1e-5
+    with pytest.raises(ValueError):
+        api.B200Simulator(M, temperature='antenna')
