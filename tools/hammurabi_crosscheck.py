@@ -120,7 +120,8 @@ def main():
     for k in keys.values():
         M.append(name=k, data=np.zeros((1, m)), otype='HEALPix')
     sim = api.B200Simulator(M, observer=OBSERVER, radial_step=args.dr, radial_max=args.r_max,
-                            cre_alpha=cre['alpha'], cre_E0=cre['E0'])
+                            cre_alpha=cre['alpha'], cre_E0=cre['E0'],
+                            temperature='cmb')          # hammurabiX reports K_CMB (docs/los_conventions.md)
     maps = {q: sim(fields)[k].data[0] for q, k in keys.items()}
     np.savez(os.path.join(args.outdir, 'b200_maps.npz'), **maps)
     sim.prepare_fields(fields, 0)                       # host copies of the summed fields, realisation 0
