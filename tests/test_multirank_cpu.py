@@ -118,3 +118,14 @@ def test_two_rank_pixel_shard_exchange():
         for k in range(K):
             for r in range(2 * n_local):
                 assert np.array_equal(full[k, r], 1000 * k + 100 * r + np.arange(plo, phi))
+
+
+def test_library_communicator_is_only_tried_where_it_applies(monkeypatch):
+    """hotpath.ensure_library_comm: single rank, a sub-group or IMB_LIBRARY_COLLECTIVES=0 never touch NCCL (and
+    never start a collective): torch.distributed stays the transport."""
+    from imagine_b200 import hotpath
+    assert hotpath.ensure_library_comm(0, 1) is False
+    assert hotpath.ensure_library_comm(0, 2, group=object()) is False
+    monkeypatch.setenv('IMB_LIBRARY_COLLECTIVES', '0')
+    assert hotpath.ensure_library_comm(0, 2) is False
+    assert hotpath._LIBRARY_COMM['tried'] is False            # none of the above counted as an attempt
