@@ -167,12 +167,12 @@ class B200Simulator(Simulator):
     masks : Masks or None -- applied INSIDE the simulator like `Hammurabi(measurements, masks=...)`
                (hammurabi.py:281-325: one identical mask covering every observable): masked pixels are not
                ray-marched at all and come back as zeros in the full-size maps
-    temperature : 'rj' (default) | 'cmb' -- Stokes I, Q, U, PI as Rayleigh-Jeans brightness temperature, which
-               is what the kernels integrate, or as thermodynamic CMB temperature, which is what hammurabiX
-               reports and the reference's key convention names ("K-cmb", observable_dict.py:15-19): a factor
-               (e^x - 1)^2 / (x^2 e^x), x = h nu / k T_cmb (1.01375 at 23 GHz).  With 'cmb' the recorded
-               hammurabiX output of tutorials/tutorial_hammurabi.ipynb is reproduced to 3e-5
-               (tools/hammurabi_tutorial_pin.py, tests/test_oracle_los.py)
+    temperature : 'cmb' (default) | 'rj' -- Stokes I, Q, U, PI as thermodynamic CMB temperature, which is what
+               hammurabiX reports and the reference's key convention names ("K-cmb", observable_dict.py:15-19),
+               or as Rayleigh-Jeans brightness temperature, which is what the kernels integrate: a factor
+               (e^x - 1)^2 / (x^2 e^x), x = h nu / k T_cmb (1.01375 at 23 GHz) applied with the unit scale of the
+               key.  With 'cmb' the recorded hammurabiX output of tutorials/tutorial_hammurabi.ipynb is
+               reproduced to 3e-5 (tools/hammurabi_tutorial_pin.py, tests/test_oracle_los.py)
     exchange : 'auto' | 'peer' | 'alltoall' | 'allgather' -- how the maps reach the likelihood on several ranks
                (hotpath.py); 'alltoall' returns pixel-sharded observables
     """
@@ -183,7 +183,7 @@ class B200Simulator(Simulator):
 
     def __init__(self, measurements, observer=(-8.3, 0.0, 0.006), radial_step=0.1, radial_max=30.0,
                  cre_alpha=3.0, cre_beta=0.0, cre_theta=0.0, cre_E0=20.6, b_stride='auto',
-                 rank=0, world=1, group=None, exchange='auto', masks=None, temperature='rj'):
+                 rank=0, world=1, group=None, exchange='auto', masks=None, temperature='cmb'):
         super().__init__(measurements)
         if temperature not in ('rj', 'cmb'):
             raise ValueError("temperature must be 'rj' (Rayleigh-Jeans brightness temperature) or 'cmb'")
@@ -262,7 +262,7 @@ class B200Simulator(Simulator):
     def _scale(self, key):
         out_unit = self.output_units.get(key)
         s = 1.0 if out_unit is None else u.unit_scale(self._units(key), out_unit)
-        if getattr(self, 'temperature', 'rj') == 'cmb' and key[0] == 'sync' and key[3] in ('I', 'Q', 'U', 'PI'):
+        if getattr(self, 'temperature', 'cmb') == 'cmb' and key[0] == 'sync' and key[3] in ('I', 'Q', 'U', 'PI'):
             s *= rj_to_cmb(float(key[1]))            # K_RJ -> K_CMB, what hammurabiX reports
         return s
 

@@ -192,9 +192,16 @@ def _los_setup(api, nside=4, N=4, res=(20, 18, 12)):
 def test_b200_simulator_matches_oracle(api):
     nside, N, res = 4, 4, (20, 18, 12)
     grid, meas, keys, fields, seeds_b = _los_setup(api, nside, N, res)
-    sim = api.B200Simulator(meas, radial_step=0.2)
+    sim = api.B200Simulator(meas, radial_step=0.2, temperature='rj')     # the oracle's (and the kernels') scale
     sims = sim(fields)
     assert isinstance(sims, api.Simulations) and set(sims.keys()) == set(keys)
+    # default: thermodynamic temperature like hammurabiX -- the same maps times the K_RJ -> K_CMB factor
+    from imagine_b200.constants import rj_to_cmb
+    cmb = api.B200Simulator(meas, radial_step=0.2)(fields)
+    assert np.array_equal(cmb[keys[0]].data, sims[keys[0]].data)                        # fd: untouched
+    assert np.allclose(cmb[keys[2]].data, sims[keys[2]].data * rj_to_cmb(23.0), rtol=1e-14, atol=0)
+    assert np.allclose(cmb[keys[5]].data, sims[keys[5]].data * rj_to_cmb(1.4), rtol=1e-14, atol=0)
+    assert np.array_equal(cmb[keys[6]].data, sims[keys[6]].data)                        # PA: an angle
     og = OF.Grid([[-20, 20], [-20, 20], [-4, 4]], res)
     stream = fields[1].device_descriptor()[2]
     descs = [(OF.CONST_B, [0, 1, 0], 0), (OF.GAUSS_B, [0, 2], stream), (OF.EXP_NE, [0.01, 3, 0.5], 0),

@@ -119,7 +119,7 @@ def test_simulator_can_report_thermodynamic_temperature():
     units = [u.rad / u.m ** 2, u.K, u.K, u.rad]
     for k, un in zip(keys, units):
         M.append(name=k, data=np.zeros((1, 48)) * un, otype='HEALPix')
-    rj, cmb = api.B200Simulator(M), api.B200Simulator(M, temperature='cmb')
+    rj, cmb = api.B200Simulator(M, temperature='rj'), api.B200Simulator(M)          # K_CMB is the default
     assert [rj._scale(k) for k in keys] == [1.0, 1.0, 1.0, 1.0]
     assert [cmb._scale(k) for k in keys] == [1.0, rj_to_cmb(23.0), rj_to_cmb(23.0), 1.0]
     assert abs(rj_to_cmb(23.0) - 1.01375) < 1e-5 and abs(rj_to_cmb(1.4) - 1.00005) < 1e-5
